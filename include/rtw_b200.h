@@ -1,0 +1,192 @@
+/*
+ * rtw_b200.h -- C-ABI of librtw_b200.so: the B200 (sm_100a) implementation of
+ * RayTracingWeekend.jl's render() -> ray_color() -> hit()/scatter() hot path.
+ *
+ * The reference (claforte/RayTracingWeekend.jl @ fe20135d) has no FFI of its own; the boundary this
+ * library sits behind is the Julia call
+ *     render(scene::HittableList, cam::Camera{T}, image_width=400, n_samples=1)   src/render.jl:8-9
+ * Julia host code (Camera/default_camera src/camera.jl:1-41, scene builders src/scenes.jl, structs
+ * src/structs.jl) stays as it is; a thin shim (raytracingweekend.jl_b200/julia/RayTracingWeekendB200.jl,
+ * shown in INTEGRATION.md) flattens the scene and `ccall`s the entry points below.  Everything is plain C:
+ * pointers, sizes, POD structs.  No C++ exception crosses this boundary; nothing here aborts the process.
+ *
+ * There is NO CPU fallback: every compute entry point needs a CUDA device and fails with an error code
+ * otherwise.
+ *
+ * Every function returns an int status: 0 = RTW_OK, < 0 = RTW_E_* below, > 0 = a cudaError_t value.
+ * rtw_last_error(ctx) returns a human-readable message for the last failure on that context.
+ */
+#ifndef RTW_B200_H
+#define RTW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTW_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RTW_API __attribute__((visibility("default")))
+#else
+#define RTW_API
+#endif
+
+#define RTW_OK 0
+#define RTW_E_INVALID_ARG (-1)   /* null pointer, non-positive size, bad device index ...            */
+#define RTW_E_NO_DEVICE (-2)     /* no CUDA device / driver: the hot path has no CPU fallback        */
+#define RTW_E_NO_SCENE (-3)      /* render called before rtw_set_scene                               */
+#define RTW_E_UNSUPPORTED (-4)   /* e.g. unknown material kind, unknown option                       */
+#define RTW_E_INTERNAL (-5)
+
+/* Material{T} subtypes, flattened (src/material.jl:3-5 Lambertian, :25-29 Metal, :37-39 Dielectric) */
+#define RTW_LAMBERTIAN 0u
+#define RTW_METAL 1u
+#define RTW_DIELECTRIC 2u
+
+/* ray_color's default `depth` (src/ray_color.jl:14) -- render() never overrides it (src/render.jl:38) */
+#define RTW_DEFAULT_MAX_DEPTH 16
+/* reseed!() at the top of every render (src/render.jl:21, src/rand.jl:2): same seed => same image */
+#define RTW_DEFAULT_SEED 1ull
+
+/*
+ * Camera{Float32}: identical field order and layout to the isbits Julia struct, src/camera.jl:1-10
+ * (7 x Vec3{Float32} + lens_radius = 22 floats = 88 bytes), so Julia passes it with Ref(cam).
+ */
+typedef struct rtw_camera {
+    float origin[3];
+    float lower_left_corner[3];
+    float horizontal[3];
+    float vertical[3];
+    float u[3];
+    float v[3];
+    float w[3];
+    float lens_radius;
+} rtw_camera;
+
+/* Work counters and device timings of the last render (what Mrays/s and the roofline are computed from). */
+typedef struct rtw_stats {
+    uint64_t paths;          /* (pixel, sample) pairs traced = rows * W * n_samples                      */
+    uint64_t ray_segments;   /* executions of hit(world, r, ...) (src/ray_color.jl:19): primary + bounces */
+    uint64_t sphere_tests;   /* ray_segments * n_spheres = executions of hit(::Sphere) (src/hit.jl:12)   */
+    uint32_t n_spheres;
+    int32_t image_width;
+    int32_t image_height;
+    int32_t rows_rendered;
+    int32_t kernel_launches; /* kernels this library launched for the call                                */
+    float ms_total;          /* CUDA-event time of the whole call on the device (incl. copies if any)     */
+    float ms_trace;          /* the trace kernel(s): raygen + intersect + shade + accumulate              */
+    float ms_resolve;        /* accumulator -> gamma-2 RGB (src/render.jl:40, src/vec.jl:22)              */
+    float ms_h2d;            /* scene / camera upload inside the call                                     */
+    float ms_d2h;            /* image download inside the call                                            */
+} rtw_stats;
+
+typedef struct rtw_ctx rtw_ctx;
+
+/* ---- options for rtw_set_option -------------------------------------------------------------- */
+#define RTW_OPT_MODE 1            /* RTW_MODE_*                                                        */
+#define RTW_OPT_STRIP 2           /* reserved (accepted, ignored)                                      */
+#define RTW_OPT_BLOCKS_PER_SM 3   /* persistent CTAs per SM (0 = library default)                      */
+#define RTW_OPT_COLLECT_TIMING 4  /* 1 = record per-stage CUDA-event timings into rtw_stats (default 1) */
+#define RTW_OPT_RAYS_PER_LANE 5   /* paths traced concurrently by one lane: 1, 2 or 4 (0 = library default) */
+#define RTW_OPT_SWEEP 6           /* RTW_SWEEP_*: inner-loop variant of the sphere-list sweep          */
+
+#define RTW_SWEEP_DEFAULT 0       /* library default (the fastest measured)                           */
+#define RTW_SWEEP_BRANCH 1        /* test + immediate root selection under a branch                    */
+#define RTW_SWEEP_MASK 2          /* sign-bit candidate masks, roots resolved after the sweep          */
+
+#define RTW_MODE_FUSED 0          /* one persistent kernel: raygen -> {intersect, shade} loop -> accumulate */
+#define RTW_MODE_WAVEFRONT 1      /* separate raygen / intersect / shade / accumulate kernels + compaction  */
+
+/* ---- life cycle ------------------------------------------------------------------------------ */
+
+RTW_API int rtw_abi_version(void);
+
+/* number of visible CUDA devices (0 and RTW_E_NO_DEVICE when there is none) */
+RTW_API int rtw_device_count(int* count);
+
+/* image height render() derives from the width: image_width div (16//9), src/render.jl:11-12 */
+RTW_API int rtw_image_height(int image_width);
+
+/*
+ * Create a context that renders on the given CUDA devices (device_ids == NULL => devices 0..n_devices-1;
+ * n_devices <= 0 => device 0 only).  Owns streams, device buffers and events; buffers grow lazily.
+ * Replaces the module-load set-up of the reference (src/init.jl:4-12).  One context is not re-entrant
+ * (calls are serialised by an internal mutex); distinct contexts are independent.
+ */
+RTW_API int rtw_create(const int* device_ids, int n_devices, rtw_ctx** out_ctx);
+RTW_API int rtw_destroy(rtw_ctx* ctx);
+RTW_API const char* rtw_last_error(const rtw_ctx* ctx);
+RTW_API int rtw_set_option(rtw_ctx* ctx, int option, int64_t value);
+
+/* ---- scene ----------------------------------------------------------------------------------- */
+
+/*
+ * Upload a flattened HittableList (src/structs.jl:10, Sphere src/structs.jl:31-35) to every device of ctx.
+ *   geom4 : n x {center.x, center.y, center.z, radius}   (radius keeps its sign: hollow glass, src/scenes.jl:35-36)
+ *   mat4  : n x {albedo.r, albedo.g, albedo.b, param}    param = fuzz (Metal) | ir (Dielectric) | 0 (Lambertian)
+ *   kind  : n x RTW_LAMBERTIAN | RTW_METAL | RTW_DIELECTRIC
+ * List order is preserved (ties in t go to the later sphere, src/hit.jl:24-26,44-46).  Host pointers;
+ * the library copies and never retains them.
+ */
+RTW_API int rtw_set_scene(rtw_ctx* ctx, const float* geom4, const float* mat4, const uint32_t* kind, uint32_t n_spheres);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+
+/*
+ * render(scene, cam, image_width, n_samples), src/render.jl:8-44, on the scene last given to rtw_set_scene.
+ *   out_rgb : HOST buffer of H*W*3 floats in the memory layout of Julia's Matrix{RGB{Float32}}(H, W)
+ *             (column-major): pixel (row i0, col j0), 0-based, at ((j0*H)+i0)*3.  Row 0 is the top row.
+ *             Values are post-gamma (sqrt, src/vec.jl:22) and unclamped, as in the reference.
+ *   max_depth : ray_color depth (reference: 16).   seed : stream seed (reference semantics: constant).
+ * Synchronous: returns after the image is in out_rgb.  Rows are split over all devices of the context
+ * (row r -> device r mod n_devices), tiles are collected on device 0.
+ */
+RTW_API int rtw_render(rtw_ctx* ctx, const rtw_camera* cam, int image_width, int n_samples, int max_depth, uint64_t seed,
+               float* out_rgb, rtw_stats* stats);
+
+/* rtw_set_scene + rtw_render in one call: exactly what the Julia method render(scene, cam, W, spp) binds to. */
+RTW_API int rtw_render_scene(rtw_ctx* ctx, const float* geom4, const float* mat4, const uint32_t* kind, uint32_t n_spheres,
+                     const rtw_camera* cam, int image_width, int n_samples, int max_depth, uint64_t seed,
+                     float* out_rgb, rtw_stats* stats);
+
+/*
+ * Device-resident variant (inputs already in HBM, output stays in HBM; used by the multi-process
+ * driver, where each rank owns one GPU, and for kernel-only timing).  Renders rows
+ *   i0 = row_start, row_start + row_stride, ...  (< H)
+ * of the image on device `device_slot` (index into the ctx's device list) and writes a compact tile
+ *   d_tile[(k*W + j0)*3 + c],  k = 0 .. n_rows-1   (row-major, post-gamma Float32)
+ * into DEVICE memory.  `stream` is a cudaStream_t (NULL = the context's own stream); the call only
+ * enqueues work on it and returns -- synchronise the stream before reading d_tile or stats.
+ * With row_start = 0, row_stride = 1 and column_major != 0 the tile is written in the Julia layout of
+ * rtw_render instead.
+ */
+RTW_API int rtw_render_rows_device(rtw_ctx* ctx, int device_slot, const rtw_camera* cam, int image_width, int n_samples,
+                           int max_depth, uint64_t seed, int row_start, int row_stride, int column_major,
+                           float* d_tile, void* stream);
+
+/* Work counters / timings of the last rtw_render_rows_device on that device (synchronises its stream). */
+RTW_API int rtw_last_stats(rtw_ctx* ctx, int device_slot, rtw_stats* stats);
+
+/*
+ * Un-interleave `n_tiles` gathered row tiles (tile g holds rows g, g+n_tiles, ...; tiles are stored
+ * back to back, each padded to ceil(H/n_tiles) rows) into the Julia column-major image.  Device
+ * pointers on device `device_slot`; enqueued on `stream`.
+ */
+RTW_API int rtw_assemble_tiles_device(rtw_ctx* ctx, int device_slot, const float* d_tiles, int n_tiles, int image_width,
+                              float* d_out_rgb, void* stream);
+
+/* ---- roofline denominator --------------------------------------------------------------------- */
+
+/*
+ * FP32 issue microbenchmark on device `device_slot`: independent FFMA chains on every SM.
+ *   variant 0: pure FFMA;  variant 1: the sweep's own mix per sphere test (3 FADD, 2 FMUL, 6 FFMA, 1 FSETP, 1 LDS.128)
+ * Writes achieved FP32 instructions/s (lane-instructions, i.e. warp instructions x 32) and the kernel time.
+ */
+RTW_API int rtw_measure_fp32_peak(rtw_ctx* ctx, int device_slot, int variant, double* fp32_instr_per_s, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTW_B200_H */

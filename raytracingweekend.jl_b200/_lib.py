@@ -1,0 +1,162 @@
+"""ctypes binding of librtw_b200.so (the C-ABI declared in include/rtw_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing, or no CUDA device is present, every
+compute entry point raises.  Nothing in this module (or package) imports or calls oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "csrc" / "librtw_b200.so"
+
+# every symbol include/rtw_b200.h declares (tests check the .so exports all of them)
+EXPORTED_SYMBOLS = (
+    "rtw_abi_version",
+    "rtw_device_count",
+    "rtw_image_height",
+    "rtw_create",
+    "rtw_destroy",
+    "rtw_last_error",
+    "rtw_set_option",
+    "rtw_set_scene",
+    "rtw_render",
+    "rtw_render_scene",
+    "rtw_render_rows_device",
+    "rtw_last_stats",
+    "rtw_assemble_tiles_device",
+    "rtw_measure_fp32_peak",
+)
+
+RTW_OK = 0
+RTW_E_INVALID_ARG = -1
+RTW_E_NO_DEVICE = -2
+RTW_E_NO_SCENE = -3
+RTW_E_UNSUPPORTED = -4
+RTW_E_INTERNAL = -5
+
+RTW_OPT_MODE = 1
+RTW_OPT_STRIP = 2
+RTW_OPT_BLOCKS_PER_SM = 3
+RTW_OPT_COLLECT_TIMING = 4
+RTW_OPT_RAYS_PER_LANE = 5
+RTW_OPT_SWEEP = 6
+
+RTW_MODE_FUSED = 0
+RTW_MODE_WAVEFRONT = 1
+
+
+class RtwError(RuntimeError):
+    """Raised for every non-zero status of the C-ABI (mirrors the Julia shim's error())."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"rtw_b200 error {code}: {message}")
+        self.code = code
+
+
+class rtw_camera(C.Structure):
+    """Camera{Float32}, src/camera.jl:1-10 -- 22 x f32, same field order."""
+
+    _fields_ = [
+        ("origin", C.c_float * 3),
+        ("lower_left_corner", C.c_float * 3),
+        ("horizontal", C.c_float * 3),
+        ("vertical", C.c_float * 3),
+        ("u", C.c_float * 3),
+        ("v", C.c_float * 3),
+        ("w", C.c_float * 3),
+        ("lens_radius", C.c_float),
+    ]
+
+
+class rtw_stats(C.Structure):
+    _fields_ = [
+        ("paths", C.c_uint64),
+        ("ray_segments", C.c_uint64),
+        ("sphere_tests", C.c_uint64),
+        ("n_spheres", C.c_uint32),
+        ("image_width", C.c_int32),
+        ("image_height", C.c_int32),
+        ("rows_rendered", C.c_int32),
+        ("kernel_launches", C.c_int32),
+        ("ms_total", C.c_float),
+        ("ms_trace", C.c_float),
+        ("ms_resolve", C.c_float),
+        ("ms_h2d", C.c_float),
+        ("ms_d2h", C.c_float),
+    ]
+
+    def as_dict(self) -> dict:
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; raise loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RtwError(
+            RTW_E_INTERNAL,
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"or raytracingweekend.jl_b200/csrc/build.sh -- there is no CPU fallback for the hot path",
+        )
+    lib = C.CDLL(os.fspath(LIB_PATH))
+    vp, i32, u32, u64, i64 = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_int64
+    fp = C.POINTER(C.c_float)
+    u32p = C.POINTER(C.c_uint32)
+    lib.rtw_abi_version.restype = i32
+    lib.rtw_abi_version.argtypes = []
+    lib.rtw_device_count.restype = i32
+    lib.rtw_device_count.argtypes = [C.POINTER(i32)]
+    lib.rtw_image_height.restype = i32
+    lib.rtw_image_height.argtypes = [i32]
+    lib.rtw_create.restype = i32
+    lib.rtw_create.argtypes = [C.POINTER(i32), i32, C.POINTER(vp)]
+    lib.rtw_destroy.restype = i32
+    lib.rtw_destroy.argtypes = [vp]
+    lib.rtw_last_error.restype = C.c_char_p
+    lib.rtw_last_error.argtypes = [vp]
+    lib.rtw_set_option.restype = i32
+    lib.rtw_set_option.argtypes = [vp, i32, i64]
+    lib.rtw_set_scene.restype = i32
+    lib.rtw_set_scene.argtypes = [vp, fp, fp, u32p, u32]
+    lib.rtw_render.restype = i32
+    lib.rtw_render.argtypes = [vp, C.POINTER(rtw_camera), i32, i32, i32, u64, fp, C.POINTER(rtw_stats)]
+    lib.rtw_render_scene.restype = i32
+    lib.rtw_render_scene.argtypes = [vp, fp, fp, u32p, u32, C.POINTER(rtw_camera), i32, i32, i32, u64, fp,
+                                     C.POINTER(rtw_stats)]
+    lib.rtw_render_rows_device.restype = i32
+    lib.rtw_render_rows_device.argtypes = [vp, i32, C.POINTER(rtw_camera), i32, i32, i32, u64, i32, i32, i32, vp, vp]
+    lib.rtw_last_stats.restype = i32
+    lib.rtw_last_stats.argtypes = [vp, i32, C.POINTER(rtw_stats)]
+    lib.rtw_assemble_tiles_device.restype = i32
+    lib.rtw_assemble_tiles_device.argtypes = [vp, i32, vp, i32, i32, vp, vp]
+    lib.rtw_measure_fp32_peak.restype = i32
+    lib.rtw_measure_fp32_peak.argtypes = [vp, i32, i32, C.POINTER(C.c_double), fp]
+    _lib = lib
+    return lib
+
+
+def check(ctx, status: int) -> None:
+    if status == RTW_OK:
+        return
+    lib = load()
+    msg = ""
+    if ctx:
+        raw = lib.rtw_last_error(ctx)
+        msg = raw.decode("utf-8", "replace") if raw else ""
+    if not msg:
+        msg = {
+            RTW_E_INVALID_ARG: "invalid argument",
+            RTW_E_NO_DEVICE: "no CUDA device visible (the hot path has no CPU fallback)",
+            RTW_E_NO_SCENE: "no scene set",
+            RTW_E_UNSUPPORTED: "unsupported",
+            RTW_E_INTERNAL: "internal error",
+        }.get(status, "CUDA error" if status > 0 else "error")
+    raise RtwError(status, msg)

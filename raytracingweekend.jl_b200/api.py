@@ -1,0 +1,170 @@
+"""render() and the Renderer context: the host side of the C-ABI boundary, mirroring
+render(scene::HittableList, cam::Camera{T}, image_width=400, n_samples=1), src/render.jl:8-9.
+
+The Julia shim (julia/RayTracingWeekendB200.jl) makes exactly the same calls with `ccall`.
+No CPU fallback: every call needs librtw_b200.so and a CUDA device, and raises RtwError otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import RtwError, rtw_camera, rtw_stats
+from .host import Camera, F32, Sphere, flatten_scene, image_height
+
+DEFAULT_MAX_DEPTH = 16  # ray_color's default depth, src/ray_color.jl:14
+DEFAULT_SEED = 1        # reseed!() semantics: the same image on every call, src/render.jl:21
+
+
+def _camera_struct(cam: Camera) -> rtw_camera:
+    if cam.elem_type != F32:
+        raise RtwError(_lib.RTW_E_UNSUPPORTED, "only Camera{Float32} is supported on the CUDA path (no CPU fallback)")
+    c = rtw_camera()
+    for name in ("origin", "lower_left_corner", "horizontal", "vertical", "u", "v", "w"):
+        arr = np.asarray(getattr(cam, name), dtype=F32)
+        getattr(c, name)[:] = [float(x) for x in arr]
+    c.lens_radius = float(cam.lens_radius)
+    return c
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class Renderer:
+    """Owns an rtw_ctx (streams, device buffers).  `devices`: list of CUDA device ids (default [0])."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None):
+        self._lib = _lib.load()
+        self._ctx = C.c_void_p()
+        devs = list(devices) if devices is not None else [0]
+        arr = (C.c_int * len(devs))(*devs)
+        status = self._lib.rtw_create(arr, len(devs), C.byref(self._ctx))
+        if status != 0:
+            self._ctx = C.c_void_p()
+            _lib.check(None, status)
+        self.devices = devs
+        self.n_spheres = 0
+        self.last_stats: Optional[dict] = None
+
+    # -- life cycle
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.rtw_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, status: int) -> None:
+        _lib.check(self._ctx, status)
+
+    def set_option(self, option: int, value: int) -> None:
+        self._check(self._lib.rtw_set_option(self._ctx, option, int(value)))
+
+    # -- scene
+    def set_scene(self, scene) -> None:
+        """scene: a HittableList (list of Sphere) or an already flattened (geom4, mat4, kind) triple."""
+        geom, mat, kind = _as_flat(scene)
+        self._check(self._lib.rtw_set_scene(self._ctx, _fp(geom), _fp(mat),
+                                            kind.ctypes.data_as(C.POINTER(C.c_uint32)), len(kind)))
+        self.n_spheres = len(kind)
+
+    # -- the hot path, host buffers (what the Julia `render` binds to)
+    def render(self, cam: Camera, image_width: int = 400, n_samples: int = 1, *, max_depth: int = DEFAULT_MAX_DEPTH,
+               seed: int = DEFAULT_SEED, scene=None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Returns the image as an (H, W, 3) float32 array view (row 0 = top), backed by a buffer in the
+        memory layout of Julia's Matrix{RGB{Float32}}(H, W).  With `scene`, the scene upload is part of the call
+        (rtw_render_scene)."""
+        W = int(image_width)
+        H = image_height(W)
+        if out is None:
+            out = np.empty((W, H, 3), dtype=F32)  # C-order (W,H,3) == column-major H x W of RGB
+        elif out.shape != (W, H, 3) or out.dtype != F32 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 array of shape (W, H, 3)")
+        cs = _camera_struct(cam)
+        st = rtw_stats()
+        if scene is not None:
+            geom, mat, kind = _as_flat(scene)
+            status = self._lib.rtw_render_scene(self._ctx, _fp(geom), _fp(mat),
+                                                kind.ctypes.data_as(C.POINTER(C.c_uint32)), len(kind), C.byref(cs), W,
+                                                int(n_samples), int(max_depth), int(seed), _fp(out), C.byref(st))
+            if status == 0:
+                self.n_spheres = len(kind)
+        else:
+            status = self._lib.rtw_render(self._ctx, C.byref(cs), W, int(n_samples), int(max_depth), int(seed),
+                                          _fp(out), C.byref(st))
+        self._check(status)
+        self.last_stats = st.as_dict()
+        return out.transpose(1, 0, 2)
+
+    # -- device-resident variants (plain device pointers; used with torch tensors as plumbing)
+    def render_rows_device(self, cam: Camera, image_width: int, n_samples: int, d_tile_ptr: int, *, max_depth: int =
+                           DEFAULT_MAX_DEPTH, seed: int = DEFAULT_SEED, row_start: int = 0, row_stride: int = 1,
+                           column_major: bool = False, stream: int = 0, device_slot: int = 0) -> None:
+        cs = _camera_struct(cam)
+        self._check(self._lib.rtw_render_rows_device(self._ctx, device_slot, C.byref(cs), int(image_width),
+                                                     int(n_samples), int(max_depth), int(seed), int(row_start),
+                                                     int(row_stride), 1 if column_major else 0,
+                                                     C.c_void_p(d_tile_ptr), C.c_void_p(stream)))
+
+    def stats(self, device_slot: int = 0) -> dict:
+        st = rtw_stats()
+        self._check(self._lib.rtw_last_stats(self._ctx, device_slot, C.byref(st)))
+        self.last_stats = st.as_dict()
+        return self.last_stats
+
+    def assemble_tiles_device(self, d_tiles_ptr: int, n_tiles: int, image_width: int, d_out_ptr: int, *,
+                              stream: int = 0, device_slot: int = 0) -> None:
+        self._check(self._lib.rtw_assemble_tiles_device(self._ctx, device_slot, C.c_void_p(d_tiles_ptr), int(n_tiles),
+                                                        int(image_width), C.c_void_p(d_out_ptr), C.c_void_p(stream)))
+
+    def measure_fp32_peak(self, variant: int = 0, device_slot: int = 0):
+        rate = C.c_double()
+        ms = C.c_float()
+        self._check(self._lib.rtw_measure_fp32_peak(self._ctx, device_slot, int(variant), C.byref(rate), C.byref(ms)))
+        return rate.value, ms.value
+
+
+def _as_flat(scene):
+    if isinstance(scene, tuple) and len(scene) == 3:
+        geom, mat, kind = scene
+    else:
+        geom, mat, kind = flatten_scene(scene)
+    geom = np.ascontiguousarray(geom, dtype=F32).reshape(-1, 4)
+    mat = np.ascontiguousarray(mat, dtype=F32).reshape(-1, 4)
+    kind = np.ascontiguousarray(kind, dtype=np.uint32).reshape(-1)
+    if not (len(geom) == len(mat) == len(kind)):
+        raise ValueError("geom4, mat4 and kind must have the same length")
+    return geom, mat, kind
+
+
+_default_renderer: Optional[Renderer] = None
+
+
+def render(scene, cam: Camera, image_width: int = 400, n_samples: int = 1, *, max_depth: int = DEFAULT_MAX_DEPTH,
+           seed: int = DEFAULT_SEED, devices: Optional[Sequence[int]] = None) -> np.ndarray:
+    """render(scene, cam, image_width=400, n_samples=1), src/render.jl:8-44, on the GPU(s).
+
+    Same positional arguments and defaults as the reference.  Keywords the reference hard-codes:
+    max_depth (ray_color's depth=16, src/ray_color.jl:14) and seed (reseed!() => constant, src/render.jl:21).
+    Returns an (H, W, 3) float32 array: img[i, j] is the reference's img[i+1, j+1] (gamma-2, unclamped)."""
+    global _default_renderer
+    if devices is not None:
+        with Renderer(devices) as r:
+            return np.array(r.render(cam, image_width, n_samples, max_depth=max_depth, seed=seed, scene=scene))
+    if _default_renderer is None:
+        _default_renderer = Renderer()
+    return _default_renderer.render(cam, image_width, n_samples, max_depth=max_depth, seed=seed, scene=scene)

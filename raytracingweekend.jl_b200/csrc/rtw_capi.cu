@@ -1,0 +1,566 @@
+// rtw_capi.cu -- the C-ABI of include/rtw_b200.h: context, buffers, streams, multi-device row split.
+// No C++ exception leaves this file; every entry point returns a status code.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rtw_b200.h"
+#include "rtw_kernels.h"
+
+namespace {
+
+struct DeviceState {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_tile = nullptr;  // tile ready (multi-device gather)
+    // scene
+    float4* d_geom = nullptr;
+    float4* d_mat = nullptr;
+    uint32_t* d_kind = nullptr;
+    size_t scene_cap = 0;
+    // render buffers
+    unsigned long long* d_accum = nullptr;
+    size_t accum_cap = 0;  // in pixels
+    unsigned long long* d_counters = nullptr;
+    unsigned long long* h_counters = nullptr;  // pinned
+    float* d_tile = nullptr;
+    size_t tile_cap = 0;  // floats
+    float* d_gather = nullptr;
+    size_t gather_cap = 0;
+    float* d_image = nullptr;
+    size_t image_cap = 0;
+    float* d_scratch = nullptr;
+    // last resident render
+    rtw_stats last = {};
+    cudaStream_t last_stream = nullptr;
+    bool last_valid = false;
+};
+
+}  // namespace
+
+struct rtw_ctx {
+    std::mutex mu;
+    std::string err;
+    std::vector<DeviceState> dev;
+    uint32_t n_spheres = 0;
+    bool have_scene = false;
+    int mode = RTW_MODE_FUSED;
+    int rays_per_lane = 0;  // 0 = default
+    int sweep = 0;          // 0 = default
+    int blocks_per_sm = 0;
+    int collect_timing = 1;
+};
+
+namespace {
+
+// defaults chosen by measurement on B200 (profiles/): see DESIGN.md "Kernel variants"
+constexpr int kDefaultRaysPerLane = 2;
+constexpr int kDefaultSweep = RTW_SWEEP_MASK;
+
+int fail(rtw_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+int cuda_fail(rtw_ctx* c, cudaError_t e, const char* what) {
+    std::string m = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    if (c) c->err = m;
+    (void)cudaGetLastError();
+    return (int)e > 0 ? (int)e : RTW_E_INTERNAL;
+}
+
+#define RTW_CUDA(ctx, call)                                   \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+template <typename T>
+int grow(rtw_ctx* c, T** p, size_t* cap, size_t need) {
+    if (need <= *cap && *p) return RTW_OK;
+    if (*p) {
+        RTW_CUDA(c, cudaFree(*p));
+        *p = nullptr;
+        *cap = 0;
+    }
+    size_t n = need ? need : 1;
+    RTW_CUDA(c, cudaMalloc((void**)p, n * sizeof(T)));
+    *cap = n;
+    return RTW_OK;
+}
+
+rtw::DevCamera to_dev_camera(const rtw_camera* c) {
+    rtw::DevCamera k;
+    k.origin = rtw::f3{c->origin[0], c->origin[1], c->origin[2]};
+    k.llc = rtw::f3{c->lower_left_corner[0], c->lower_left_corner[1], c->lower_left_corner[2]};
+    k.horizontal = rtw::f3{c->horizontal[0], c->horizontal[1], c->horizontal[2]};
+    k.vertical = rtw::f3{c->vertical[0], c->vertical[1], c->vertical[2]};
+    k.u = rtw::f3{c->u[0], c->u[1], c->u[2]};
+    k.v = rtw::f3{c->v[0], c->v[1], c->v[2]};
+    k.lens_radius = c->lens_radius;
+    return k;
+}
+
+int rows_of(int H, int row_start, int row_stride) {
+    if (row_start >= H) return 0;
+    return (H - row_start + row_stride - 1) / row_stride;
+}
+
+// fixed-point fraction bits of the accumulator: 62 bits total, minus ceil(log2(spp)), minus 6 bits (64x) of
+// head-room for per-path radiance above 1 (the reference's scenes never exceed 1: albedo and sky are <= 1).
+int fx_bits_for(int spp) {
+    int b = 0;
+    while ((1ll << b) < (long long)spp) ++b;
+    return 62 - b - 6;
+}
+
+int check_render_args(rtw_ctx* ctx, const rtw_camera* cam, int W, int spp, int max_depth) {
+    if (!cam) return fail(ctx, RTW_E_INVALID_ARG, "camera is NULL");
+    if (W < 1 || W > 65536) return fail(ctx, RTW_E_INVALID_ARG, "image_width must be in 1..65536");
+    if (spp < 1 || spp > (1 << 24)) return fail(ctx, RTW_E_INVALID_ARG, "n_samples must be in 1..2^24");
+    if (max_depth < 0 || max_depth > (1 << 20)) return fail(ctx, RTW_E_INVALID_ARG, "max_depth must be in 0..2^20");
+    if (!ctx->have_scene) return fail(ctx, RTW_E_NO_SCENE, "rtw_set_scene has not been called");
+    return RTW_OK;
+}
+
+// Enqueue trace + resolve for a row subset on one device.  Output: d_out (tile row-major, or Julia column-major).
+int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, int spp, int max_depth, uint64_t seed,
+                 int row_start, int row_stride, int column_major, float* d_out, cudaStream_t stream, bool timing) {
+    const int H = rtw_image_height(W);
+    const int n_rows = rows_of(H, row_start, row_stride);
+    RTW_CUDA(ctx, cudaSetDevice(ds.device));
+    ds.last = rtw_stats{};
+    ds.last.n_spheres = ctx->n_spheres;
+    ds.last.image_width = W;
+    ds.last.image_height = H;
+    ds.last.rows_rendered = n_rows;
+    ds.last.paths = (uint64_t)n_rows * (uint64_t)W * (uint64_t)spp;
+    ds.last_stream = stream;
+    ds.last_valid = true;
+    if (n_rows == 0 || H == 0) return RTW_OK;
+
+    const size_t npix = (size_t)n_rows * (size_t)W;
+    int rc = grow(ctx, &ds.d_accum, &ds.accum_cap, npix * 4);
+    if (rc) return rc;
+    if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[0], stream));
+    RTW_CUDA(ctx, cudaMemsetAsync(ds.d_accum, 0, npix * 4 * sizeof(unsigned long long), stream));
+    RTW_CUDA(ctx, cudaMemsetAsync(ds.d_counters, 0, 2 * sizeof(unsigned long long), stream));
+
+    const int fx_bits = fx_bits_for(spp);
+    int launches = 0;
+    if (max_depth > 0) {
+        rtw::TraceParams p;
+        p.cam = to_dev_camera(cam);
+        p.geom = ds.d_geom;
+        p.mat = ds.d_mat;
+        p.kind = ds.d_kind;
+        p.n_spheres = ctx->n_spheres;
+        p.W = W; p.H = H; p.spp = spp; p.max_depth = max_depth;
+        p.key0 = (uint32_t)seed; p.key1 = (uint32_t)(seed >> 32);
+        p.row_start = row_start; p.row_stride = row_stride; p.n_rows = n_rows;
+        p.n_paths = (unsigned long long)npix * (unsigned long long)spp;
+        p.accum = ds.d_accum;
+        p.fx_scale = std::ldexp(1.0, fx_bits);
+        p.counters = ds.d_counters;
+        rtw::LaunchInfo li{};
+        const int rays = ctx->rays_per_lane > 0 ? ctx->rays_per_lane : kDefaultRaysPerLane;
+        const int sweep = ctx->sweep > 0 ? ctx->sweep : kDefaultSweep;
+        RTW_CUDA(ctx, rtw::launch_fused_trace(p, ds.num_sms, ctx->blocks_per_sm, rays, sweep, stream, &li));
+        launches += li.launches;
+    }
+    if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[1], stream));
+    RTW_CUDA(ctx, rtw::launch_resolve(ds.d_accum, W, H, n_rows, row_start, row_stride, spp, std::ldexp(1.0, -fx_bits),
+                                      column_major, d_out, stream));
+    launches += 1;
+    if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[2], stream));
+    RTW_CUDA(ctx, cudaMemcpyAsync(ds.h_counters, ds.d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                  stream));
+    ds.last.kernel_launches = launches;
+    return RTW_OK;
+}
+
+// after the stream has been synchronised: fill counters / timings
+int finish_stats(rtw_ctx* ctx, DeviceState& ds, bool timing) {
+    ds.last.ray_segments = ds.h_counters[1];
+    ds.last.sphere_tests = ds.last.ray_segments * (uint64_t)ctx->n_spheres;
+    if (timing && ds.last.rows_rendered > 0) {
+        float a = 0.f, b = 0.f;
+        RTW_CUDA(ctx, cudaEventElapsedTime(&a, ds.ev[0], ds.ev[1]));
+        RTW_CUDA(ctx, cudaEventElapsedTime(&b, ds.ev[1], ds.ev[2]));
+        ds.last.ms_trace = a;
+        ds.last.ms_resolve = b;
+        ds.last.ms_total = a + b;
+    }
+    return RTW_OK;
+}
+
+int set_scene_locked(rtw_ctx* ctx, const float* geom4, const float* mat4, const uint32_t* kind, uint32_t n) {
+    if (n > 0 && (!geom4 || !mat4 || !kind)) return fail(ctx, RTW_E_INVALID_ARG, "scene arrays are NULL");
+    if (n > (1u << 26)) return fail(ctx, RTW_E_INVALID_ARG, "too many spheres");
+    for (uint32_t i = 0; i < n; ++i)
+        if (kind[i] > RTW_DIELECTRIC) return fail(ctx, RTW_E_UNSUPPORTED, "unknown material kind (only Lambertian/Metal/Dielectric)");
+    for (auto& ds : ctx->dev) {
+        RTW_CUDA(ctx, cudaSetDevice(ds.device));
+        if (n > ds.scene_cap || !ds.d_geom) {
+            if (ds.d_geom) cudaFree(ds.d_geom);
+            if (ds.d_mat) cudaFree(ds.d_mat);
+            if (ds.d_kind) cudaFree(ds.d_kind);
+            ds.d_geom = nullptr; ds.d_mat = nullptr; ds.d_kind = nullptr; ds.scene_cap = 0;
+            size_t cap = n ? n : 1;
+            RTW_CUDA(ctx, cudaMalloc((void**)&ds.d_geom, cap * sizeof(float4)));
+            RTW_CUDA(ctx, cudaMalloc((void**)&ds.d_mat, cap * sizeof(float4)));
+            RTW_CUDA(ctx, cudaMalloc((void**)&ds.d_kind, cap * sizeof(uint32_t)));
+            ds.scene_cap = cap;
+        }
+        if (n) {
+            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_geom, geom4, (size_t)n * 16, cudaMemcpyHostToDevice, ds.stream));
+            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_mat, mat4, (size_t)n * 16, cudaMemcpyHostToDevice, ds.stream));
+            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_kind, kind, (size_t)n * 4, cudaMemcpyHostToDevice, ds.stream));
+        }
+    }
+    for (auto& ds : ctx->dev) {
+        RTW_CUDA(ctx, cudaSetDevice(ds.device));
+        RTW_CUDA(ctx, cudaStreamSynchronize(ds.stream));  // host arrays may be freed by the caller after return
+    }
+    ctx->n_spheres = n;
+    ctx->have_scene = true;
+    return RTW_OK;
+}
+
+int render_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int spp, int max_depth, uint64_t seed, float* out_rgb,
+                  rtw_stats* stats, bool scene_uploaded_in_call) {
+    int rc = check_render_args(ctx, cam, W, spp, max_depth);
+    if (rc) return rc;
+    if (!out_rgb) return fail(ctx, RTW_E_INVALID_ARG, "out_rgb is NULL");
+    const int H = rtw_image_height(W);
+    const int G = (int)ctx->dev.size();
+    const size_t img_floats = (size_t)W * (size_t)H * 3;
+    DeviceState& d0 = ctx->dev[0];
+    const bool timing = ctx->collect_timing != 0;
+    RTW_CUDA(ctx, cudaSetDevice(d0.device));
+    rc = grow(ctx, &d0.d_image, &d0.image_cap, img_floats);
+    if (rc) return rc;
+    // ev[3] = start of the call (recorded by rtw_render_scene before the upload when the scene travels with it)
+    if (!scene_uploaded_in_call) RTW_CUDA(ctx, cudaEventRecord(d0.ev[3], d0.stream));
+    RTW_CUDA(ctx, cudaEventRecord(d0.ev[6], d0.stream));
+    if (G == 1) {
+        rc = enqueue_rows(ctx, d0, cam, W, spp, max_depth, seed, 0, 1, 1, d0.d_image, d0.stream, timing);
+        if (rc) return rc;
+    } else {
+        const int rows_pad = (H + G - 1) / G;
+        const size_t tile_floats = (size_t)rows_pad * W * 3;
+        rc = grow(ctx, &d0.d_gather, &d0.gather_cap, tile_floats * G);
+        if (rc) return rc;
+        for (int g = 0; g < G; ++g) {
+            DeviceState& ds = ctx->dev[g];
+            RTW_CUDA(ctx, cudaSetDevice(ds.device));
+            float* dst = d0.d_gather + tile_floats * g;
+            float* tile = dst;
+            if (g != 0) {
+                rc = grow(ctx, &ds.d_tile, &ds.tile_cap, tile_floats);
+                if (rc) return rc;
+                tile = ds.d_tile;
+            }
+            rc = enqueue_rows(ctx, ds, cam, W, spp, max_depth, seed, g, G, 0, tile, ds.stream, timing);
+            if (rc) return rc;
+            if (g != 0) {
+                // framebuffer gather: tile -> device 0 over NVLink (peer copy on the producer's stream)
+                size_t bytes = (size_t)rows_of(H, g, G) * W * 3 * sizeof(float);
+                if (bytes) RTW_CUDA(ctx, cudaMemcpyPeerAsync(dst, d0.device, tile, ds.device, bytes, ds.stream));
+                RTW_CUDA(ctx, cudaEventRecord(ds.ev_tile, ds.stream));
+            }
+        }
+        RTW_CUDA(ctx, cudaSetDevice(d0.device));
+        for (int g = 1; g < G; ++g) RTW_CUDA(ctx, cudaStreamWaitEvent(d0.stream, ctx->dev[g].ev_tile, 0));
+        RTW_CUDA(ctx, rtw::launch_assemble(d0.d_gather, G, W, H, d0.d_image, d0.stream));
+    }
+    RTW_CUDA(ctx, cudaEventRecord(d0.ev[4], d0.stream));
+    if (img_floats)
+        RTW_CUDA(ctx, cudaMemcpyAsync(out_rgb, d0.d_image, img_floats * sizeof(float), cudaMemcpyDeviceToHost, d0.stream));
+    RTW_CUDA(ctx, cudaEventRecord(d0.ev[5], d0.stream));
+    for (int g = G - 1; g >= 0; --g) {
+        RTW_CUDA(ctx, cudaSetDevice(ctx->dev[g].device));
+        RTW_CUDA(ctx, cudaStreamSynchronize(ctx->dev[g].stream));
+    }
+    rtw_stats total = {};
+    total.n_spheres = ctx->n_spheres;
+    total.image_width = W;
+    total.image_height = H;
+    for (int g = 0; g < G; ++g) {
+        DeviceState& ds = ctx->dev[g];
+        RTW_CUDA(ctx, cudaSetDevice(ds.device));
+        rc = finish_stats(ctx, ds, timing);
+        if (rc) return rc;
+        total.paths += ds.last.paths;
+        total.ray_segments += ds.last.ray_segments;
+        total.sphere_tests += ds.last.sphere_tests;
+        total.rows_rendered += ds.last.rows_rendered;
+        total.kernel_launches += ds.last.kernel_launches;
+        total.ms_trace = std::fmax(total.ms_trace, ds.last.ms_trace);
+        total.ms_resolve = std::fmax(total.ms_resolve, ds.last.ms_resolve);
+    }
+    if (G > 1) total.kernel_launches += 1;
+    RTW_CUDA(ctx, cudaSetDevice(d0.device));
+    float ms = 0.f;
+    RTW_CUDA(ctx, cudaEventElapsedTime(&ms, d0.ev[3], d0.ev[5]));
+    total.ms_total = ms;
+    RTW_CUDA(ctx, cudaEventElapsedTime(&ms, d0.ev[4], d0.ev[5]));
+    total.ms_d2h = ms;
+    RTW_CUDA(ctx, cudaEventElapsedTime(&ms, d0.ev[3], d0.ev[6]));
+    total.ms_h2d = ms;
+    if (stats) *stats = total;
+    return RTW_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ C-ABI
+
+extern "C" {
+
+int rtw_abi_version(void) { return RTW_ABI_VERSION; }
+
+int rtw_image_height(int image_width) {
+    if (image_width < 0) return 0;
+    return (int)(((long long)image_width * 9) / 16);  // image_width div (16//9), src/render.jl:11-12
+}
+
+int rtw_device_count(int* count) {
+    if (!count) return RTW_E_INVALID_ARG;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        *count = 0;
+        return RTW_E_NO_DEVICE;
+    }
+    *count = n;
+    return RTW_OK;
+}
+
+int rtw_create(const int* device_ids, int n_devices, rtw_ctx** out_ctx) {
+    if (!out_ctx) return RTW_E_INVALID_ARG;
+    *out_ctx = nullptr;
+    int visible = 0;
+    int rc = rtw_device_count(&visible);
+    if (rc) return rc;
+    if (n_devices <= 0) n_devices = 1;
+    if (n_devices > visible) return RTW_E_INVALID_ARG;
+    rtw_ctx* ctx = new (std::nothrow) rtw_ctx();
+    if (!ctx) return RTW_E_INTERNAL;
+    try {
+        ctx->dev.resize((size_t)n_devices);
+    } catch (...) {
+        delete ctx;
+        return RTW_E_INTERNAL;
+    }
+    for (int g = 0; g < n_devices; ++g) {
+        DeviceState& ds = ctx->dev[g];
+        ds.device = device_ids ? device_ids[g] : g;
+        if (ds.device < 0 || ds.device >= visible) {
+            rtw_destroy(ctx);
+            return RTW_E_INVALID_ARG;
+        }
+        cudaError_t e = cudaSetDevice(ds.device);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ds.num_sms, cudaDevAttrMultiProcessorCount, ds.device);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ds.stream, cudaStreamNonBlocking);
+        for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&ds.ev[i]);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ds.ev_tile, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&ds.d_counters, 2 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&ds.h_counters, 2 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&ds.d_scratch, 4u << 20);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            rtw_destroy(ctx);
+            return (int)e;
+        }
+        ds.h_counters[0] = ds.h_counters[1] = 0;
+    }
+    // enable peer access towards device 0 for the tile gather (ignored when unavailable: the copy is then staged)
+    for (int g = 1; g < n_devices; ++g) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, ctx->dev[g].device, ctx->dev[0].device) == cudaSuccess && can) {
+            cudaSetDevice(ctx->dev[g].device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctx->dev[0].device, 0);
+            if (e != cudaSuccess) (void)cudaGetLastError();
+        }
+    }
+    *out_ctx = ctx;
+    return RTW_OK;
+}
+
+int rtw_destroy(rtw_ctx* ctx) {
+    if (!ctx) return RTW_OK;
+    for (auto& ds : ctx->dev) {
+        if (cudaSetDevice(ds.device) != cudaSuccess) continue;
+        if (ds.stream) cudaStreamSynchronize(ds.stream);
+        cudaFree(ds.d_geom); cudaFree(ds.d_mat); cudaFree(ds.d_kind);
+        cudaFree(ds.d_accum); cudaFree(ds.d_counters); cudaFree(ds.d_tile);
+        cudaFree(ds.d_gather); cudaFree(ds.d_image); cudaFree(ds.d_scratch);
+        if (ds.h_counters) cudaFreeHost(ds.h_counters);
+        for (auto& e : ds.ev) if (e) cudaEventDestroy(e);
+        if (ds.ev_tile) cudaEventDestroy(ds.ev_tile);
+        if (ds.stream) cudaStreamDestroy(ds.stream);
+    }
+    (void)cudaGetLastError();
+    delete ctx;
+    return RTW_OK;
+}
+
+const char* rtw_last_error(const rtw_ctx* ctx) { return ctx ? ctx->err.c_str() : "rtw_ctx is NULL"; }
+
+int rtw_set_option(rtw_ctx* ctx, int option, int64_t value) {
+    if (!ctx) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    switch (option) {
+        case RTW_OPT_MODE:
+            if (value != RTW_MODE_FUSED) return fail(ctx, RTW_E_UNSUPPORTED, "only RTW_MODE_FUSED is implemented");
+            ctx->mode = (int)value;
+            return RTW_OK;
+        case RTW_OPT_STRIP:
+            return RTW_OK;  // accepted for ABI compatibility; paths are flushed individually since ABI v1
+        case RTW_OPT_RAYS_PER_LANE:
+            if (value != 0 && value != 1 && value != 2 && value != 4)
+                return fail(ctx, RTW_E_INVALID_ARG, "rays_per_lane must be 0 (default), 1, 2 or 4");
+            ctx->rays_per_lane = (int)value;
+            return RTW_OK;
+        case RTW_OPT_SWEEP:
+            if (value < 0 || value > RTW_SWEEP_MASK) return fail(ctx, RTW_E_INVALID_ARG, "unknown sweep variant");
+            ctx->sweep = (int)value;
+            return RTW_OK;
+        case RTW_OPT_BLOCKS_PER_SM:
+            if (value < 0 || value > 32) return fail(ctx, RTW_E_INVALID_ARG, "blocks_per_sm must be in 0..32");
+            ctx->blocks_per_sm = (int)value;
+            return RTW_OK;
+        case RTW_OPT_COLLECT_TIMING:
+            ctx->collect_timing = value != 0;
+            return RTW_OK;
+        default:
+            return fail(ctx, RTW_E_UNSUPPORTED, "unknown option");
+    }
+}
+
+int rtw_set_scene(rtw_ctx* ctx, const float* geom4, const float* mat4, const uint32_t* kind, uint32_t n_spheres) {
+    if (!ctx) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    try {
+        return set_scene_locked(ctx, geom4, mat4, kind, n_spheres);
+    } catch (...) {
+        return fail(ctx, RTW_E_INTERNAL, "unexpected C++ exception in rtw_set_scene");
+    }
+}
+
+int rtw_render(rtw_ctx* ctx, const rtw_camera* cam, int image_width, int n_samples, int max_depth, uint64_t seed,
+               float* out_rgb, rtw_stats* stats) {
+    if (!ctx) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    try {
+        return render_locked(ctx, cam, image_width, n_samples, max_depth, seed, out_rgb, stats, false);
+    } catch (...) {
+        return fail(ctx, RTW_E_INTERNAL, "unexpected C++ exception in rtw_render");
+    }
+}
+
+int rtw_render_scene(rtw_ctx* ctx, const float* geom4, const float* mat4, const uint32_t* kind, uint32_t n_spheres,
+                     const rtw_camera* cam, int image_width, int n_samples, int max_depth, uint64_t seed,
+                     float* out_rgb, rtw_stats* stats) {
+    if (!ctx) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    try {
+        DeviceState& d0 = ctx->dev[0];
+        RTW_CUDA(ctx, cudaSetDevice(d0.device));
+        RTW_CUDA(ctx, cudaEventRecord(d0.ev[3], d0.stream));
+        int rc = set_scene_locked(ctx, geom4, mat4, kind, n_spheres);
+        if (rc) return rc;
+        return render_locked(ctx, cam, image_width, n_samples, max_depth, seed, out_rgb, stats, true);
+    } catch (...) {
+        return fail(ctx, RTW_E_INTERNAL, "unexpected C++ exception in rtw_render_scene");
+    }
+}
+
+int rtw_render_rows_device(rtw_ctx* ctx, int device_slot, const rtw_camera* cam, int image_width, int n_samples,
+                           int max_depth, uint64_t seed, int row_start, int row_stride, int column_major,
+                           float* d_tile, void* stream) {
+    if (!ctx) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    try {
+        if (device_slot < 0 || device_slot >= (int)ctx->dev.size()) return fail(ctx, RTW_E_INVALID_ARG, "bad device_slot");
+        int rc = check_render_args(ctx, cam, image_width, n_samples, max_depth);
+        if (rc) return rc;
+        if (!d_tile) return fail(ctx, RTW_E_INVALID_ARG, "d_tile is NULL");
+        if (row_start < 0 || row_stride < 1) return fail(ctx, RTW_E_INVALID_ARG, "bad row_start/row_stride");
+        if (column_major && (row_start != 0 || row_stride != 1))
+            return fail(ctx, RTW_E_INVALID_ARG, "column_major output needs row_start=0,row_stride=1");
+        DeviceState& ds = ctx->dev[device_slot];
+        cudaStream_t s = stream ? (cudaStream_t)stream : ds.stream;
+        return enqueue_rows(ctx, ds, cam, image_width, n_samples, max_depth, seed, row_start, row_stride, column_major,
+                            d_tile, s, ctx->collect_timing != 0);
+    } catch (...) {
+        return fail(ctx, RTW_E_INTERNAL, "unexpected C++ exception in rtw_render_rows_device");
+    }
+}
+
+int rtw_last_stats(rtw_ctx* ctx, int device_slot, rtw_stats* stats) {
+    if (!ctx || !stats) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (device_slot < 0 || device_slot >= (int)ctx->dev.size()) return fail(ctx, RTW_E_INVALID_ARG, "bad device_slot");
+    DeviceState& ds = ctx->dev[device_slot];
+    if (!ds.last_valid) return fail(ctx, RTW_E_INVALID_ARG, "no render has been enqueued on this device");
+    RTW_CUDA(ctx, cudaSetDevice(ds.device));
+    RTW_CUDA(ctx, cudaStreamSynchronize(ds.last_stream ? ds.last_stream : ds.stream));
+    int rc = finish_stats(ctx, ds, ctx->collect_timing != 0);
+    if (rc) return rc;
+    *stats = ds.last;
+    return RTW_OK;
+}
+
+int rtw_assemble_tiles_device(rtw_ctx* ctx, int device_slot, const float* d_tiles, int n_tiles, int image_width,
+                              float* d_out_rgb, void* stream) {
+    if (!ctx) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (device_slot < 0 || device_slot >= (int)ctx->dev.size()) return fail(ctx, RTW_E_INVALID_ARG, "bad device_slot");
+    if (!d_tiles || !d_out_rgb || n_tiles < 1 || image_width < 1) return fail(ctx, RTW_E_INVALID_ARG, "bad arguments");
+    DeviceState& ds = ctx->dev[device_slot];
+    RTW_CUDA(ctx, cudaSetDevice(ds.device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ds.stream;
+    RTW_CUDA(ctx, rtw::launch_assemble(d_tiles, n_tiles, image_width, rtw_image_height(image_width), d_out_rgb, s));
+    return RTW_OK;
+}
+
+int rtw_measure_fp32_peak(rtw_ctx* ctx, int device_slot, int variant, double* fp32_instr_per_s, float* ms_out) {
+    if (!ctx || !fp32_instr_per_s) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (device_slot < 0 || device_slot >= (int)ctx->dev.size()) return fail(ctx, RTW_E_INVALID_ARG, "bad device_slot");
+    if (variant < 0 || variant > 1) return fail(ctx, RTW_E_INVALID_ARG, "variant must be 0 or 1");
+    DeviceState& ds = ctx->dev[device_slot];
+    RTW_CUDA(ctx, cudaSetDevice(ds.device));
+    double instr = 0.0, best = 0.0;
+    float best_ms = 0.f;
+    const float ray[6] = {0.125f, 0.25f, 0.5f, 0.6f, 0.0f, 0.8f};  // origin, unit direction
+    RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_scratch, ray, sizeof ray, cudaMemcpyHostToDevice, ds.stream));
+    for (int rep = 0; rep < 5; ++rep) {  // rep 0 is the warm-up
+        RTW_CUDA(ctx, cudaEventRecord(ds.ev[0], ds.stream));
+        RTW_CUDA(ctx, rtw::launch_fp32_peak(variant, ds.num_sms, ds.d_scratch, ds.stream, &instr));
+        RTW_CUDA(ctx, cudaEventRecord(ds.ev[1], ds.stream));
+        RTW_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+        float ms = 0.f;
+        RTW_CUDA(ctx, cudaEventElapsedTime(&ms, ds.ev[0], ds.ev[1]));
+        if (rep > 0 && ms > 0.f) {
+            double r = instr / (ms * 1e-3);
+            if (r > best) { best = r; best_ms = ms; }
+        }
+    }
+    *fp32_instr_per_s = best;
+    if (ms_out) *ms_out = best_ms;
+    return RTW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,536 @@
+// rtw_kernels.cu -- hand-written sm_100a kernels of the render hot path.
+//
+//   fused_trace_kernel : persistent-threads wavefront.  Every lane owns one path; the CTA-resident loop is
+//                        regenerate (raygen, src/render.jl:26-37 + src/camera.jl:43-48)
+//                        -> intersect (closest-hit sweep over the sphere list, src/hit.jl:38-50, 12-35)
+//                        -> shade/scatter (src/material.jl, src/light.jl, src/ray_color.jl:1-6, 14-37)
+//                        -> accumulate (src/render.jl:38).  Finished lanes are refilled from a ticket counter
+//                        (warp ballot + prefix), so the sweep always runs on dense warps.
+//   resolve_kernel     : accum/n_samples, gamma-2, store in Julia column-major (src/render.jl:40, src/vec.jl:22)
+//   assemble_kernel    : un-interleave gathered row tiles (multi-GPU)
+//   fp32_peak_kernel   : roofline denominators (FP32 issue rate)
+//
+// Compiled with -fmad=false; see rtw_device.cuh for the FP contract.
+#include "rtw_kernels.h"
+
+namespace rtw {
+
+namespace {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kTraceBlock = 256;
+constexpr unsigned kPoolChunk = 128;  // path tickets a warp takes from the global counter at a time
+
+// ---- 1-D bulk TMA (cp.async.bulk, SASS UBLKCP) + mbarrier helpers ------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes,
+                                             unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ---- closest-hit sweep over one shared-memory tile of the sphere list (src/hit.jl:38-50) -------------------
+// Every lane traces R independent paths ("slots"); one broadcast LDS.128 of a sphere feeds R tests.
+
+// RTW_SWEEP_BRANCH: test, and select the root at once under a (rare, divergent) branch.
+template <int R>
+__device__ __forceinline__ void sweep_tile_branch(const float4* __restrict__ tile, uint32_t count, uint32_t k_base,
+                                                  const f3 (&o)[R], const f3 (&d)[R], const bool (&alive)[R],
+                                                  float (&best_t)[R], int (&best_k)[R]) {
+    const float tmin = 1e-4f;  // T(1e-4), src/ray_color.jl:19
+#pragma unroll 4
+    for (uint32_t k = 0; k < count; ++k) {
+        float4 s = tile[k];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float hb;
+            float disc = sphere_disc(s, o[r], d[r], hb);
+            if (!(disc < 0.0f) && alive[r]) {  // src/hit.jl:19
+                if (sphere_accept(disc, hb, tmin, best_t[r])) best_k[r] = (int)(k_base + k);
+            }
+        }
+    }
+}
+
+// RTW_SWEEP_MASK: the inner loop is branch-free -- per test 11 FP32 instructions + one funnel shift that
+// pushes the sign bit of the discriminant (set = miss, src/hit.jl:19) into a per-slot 32-test mask.  Masks go
+// to shared memory once per 32 tests; after the tile each lane walks only its own candidates (in list order,
+// so ties still go to the later sphere) and redoes the identical arithmetic to select the root.
+// (A NaN discriminant -- only reachable with non-finite scene/camera values -- counts as a miss when its
+// sign bit is set; the reference would treat it as a hit.)
+template <int R, int kBlock>
+__device__ __forceinline__ void sweep_tile_mask(const float4* __restrict__ tile, uint32_t count, uint32_t k_base,
+                                                uint32_t* __restrict__ s_mask, const f3 (&o)[R], const f3 (&d)[R],
+                                                const bool (&alive)[R], float (&best_t)[R], int (&best_k)[R]) {
+    const float tmin = 1e-4f;
+    const uint32_t nchunks = (count + 31u) >> 5;
+    uint32_t summary[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) summary[r] = 0u;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const float4* ch = tile + c * 32u;
+        uint32_t m[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) m[r] = 0u;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float4 s = ch[j];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float hb;
+                float disc = sphere_disc(s, o[r], d[r], hb);
+                m[r] = __funnelshift_l(__float_as_uint(disc), m[r], 1);  // test j of the chunk ends at bit 31-j
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            s_mask[(c * R + r) * kBlock] = m[r];
+            summary[r] |= (m[r] != 0xffffffffu ? 1u : 0u) << c;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (!alive[r]) continue;
+        uint32_t sum = summary[r], cand = 0u, c = 0u;
+        for (;;) {
+            if (cand == 0u) {
+                if (sum == 0u) break;
+                c = (uint32_t)__ffs((int)sum) - 1u;
+                sum &= sum - 1u;
+                cand = ~s_mask[(c * R + r) * kBlock];
+                uint32_t valid = count - c * 32u;  // entries of the last chunk beyond `count` are padding
+                if (valid < 32u) cand &= 0xffffffffu << (32u - valid);
+                if (cand == 0u) continue;
+            }
+            uint32_t j = (uint32_t)__clz((int)cand);
+            cand &= ~(0x80000000u >> j);
+            uint32_t kl = c * 32u + j;
+            float4 s = tile[kl];
+            float hb;
+            float disc = sphere_disc(s, o[r], d[r], hb);  // bit-identical to the value computed in the sweep
+            if (sphere_accept(disc, hb, tmin, best_t[r])) best_k[r] = (int)(k_base + kl);
+        }
+    }
+}
+
+// ---- the persistent fused kernel ------------------------------------------------------------------------------
+// kMulti = false: the whole list (<= kTileSpheres) is staged once; warps then run free of CTA barriers.
+// kMulti = true : the list is streamed per bounce through two 16 KB TMA buffers, CTA-synchronously.
+template <int R, int SWEEP, bool kMulti>
+__global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
+    fused_trace_kernel(const __grid_constant__ TraceParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    const uint32_t n = P.n_spheres;
+    const uint32_t n_tiles = kMulti ? (n + kTileSpheres - 1u) / kTileSpheres : 1u;
+    const uint32_t tile_cap = kMulti ? kTileSpheres : ((n + 31u) & ~31u);  // spheres per buffer (multiple of 32)
+    float4* s_tile0 = reinterpret_cast<float4*>(smem_raw);
+    float4* s_tile1 = s_tile0 + tile_cap;
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tile0 + (kMulti ? 2u : 1u) * tile_cap) + threadIdx.x;
+
+    // zero the tile buffers once (padding entries are read by the unrolled sweep and then masked off)
+    for (uint32_t i = threadIdx.x; i < (kMulti ? 2u : 1u) * tile_cap; i += kTraceBlock)
+        s_tile0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+    }
+    // generic-proxy writes (the zero fill) must be ordered before the async-proxy (TMA) writes to the same bytes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    uint32_t bar_phase0 = 0u, bar_phase1 = 0u;
+    if (!kMulti) {
+        if (threadIdx.x == 0 && n > 0u) {
+            mbar_arrive_expect_tx(&s_bar[0], n * 16u);
+            tma_bulk_g2s(s_tile0, P.geom, n * 16u, &s_bar[0]);
+        }
+        if (n > 0u) mbar_wait(&s_bar[0], 0u);
+    }
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t k0 = P.key0, k1 = P.key1;
+
+    // per-slot path state
+    f3 o[R], d[R];
+    double thr_r[R], thr_g[R], thr_b[R];  // product of attenuations so far (Float64, as the reference promotes)
+    uint32_t pix_local[R];
+    int depth_left[R];
+    bool alive[R];
+    PathRng rng[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        o[r] = mk3(0.f, 0.f, 0.f);
+        d[r] = mk3(0.f, 1.f, 0.f);
+        thr_r[r] = thr_g[r] = thr_b[r] = 1.0;
+        pix_local[r] = 0u;
+        depth_left[r] = 0;
+        alive[r] = false;
+        rng_begin(rng[r], 0u, 0u);
+    }
+    bool done = false;  // lane-level: no more tickets
+    uint32_t seg_count = 0;
+    // warp-level ticket pool (uniform)
+    unsigned long long pool_next = 0, pool_end = 0;
+    bool exhausted = false;
+
+    for (;;) {
+        // ------------------------------------------------------------ regenerate: idle slots take the next path
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            bool want = !alive[r] && !done;
+            unsigned pending = __ballot_sync(kFullMask, want);
+            if (pending == 0u) continue;
+            unsigned long long ticket = 0;
+            bool got = false;
+            while (pending) {
+                if (exhausted) {
+                    if (want) { done = true; want = false; }
+                    break;
+                }
+                if (pool_next >= pool_end) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(P.counters, (unsigned long long)kPoolChunk);
+                    base = __shfl_sync(kFullMask, base, 0);
+                    if (base >= P.n_paths) { exhausted = true; continue; }
+                    pool_next = base;
+                    pool_end = base + kPoolChunk < P.n_paths ? base + kPoolChunk : P.n_paths;
+                }
+                unsigned avail = (unsigned)(pool_end - pool_next);
+                unsigned rank = __popc(pending & lt_mask);
+                if (want && rank < avail) { ticket = pool_next + rank; want = false; got = true; }
+                unsigned npend = __popc(pending);
+                pool_next += npend < avail ? npend : avail;
+                pending = __ballot_sync(kFullMask, want);
+            }
+            if (got) {
+                // ticket -> (pixel, sample): consecutive tickets are consecutive samples of one pixel
+                uint32_t pl, s0;
+                if ((P.n_paths >> 32) == 0ull) {
+                    pl = (uint32_t)ticket / (uint32_t)P.spp;
+                    s0 = (uint32_t)ticket - pl * (uint32_t)P.spp;
+                } else {
+                    unsigned long long q = ticket / (unsigned)P.spp;
+                    pl = (uint32_t)q;
+                    s0 = (uint32_t)(ticket - q * (unsigned)P.spp);
+                }
+                uint32_t row_local = pl / (uint32_t)P.W;
+                uint32_t col = pl - row_local * (uint32_t)P.W;
+                uint32_t i0 = (uint32_t)P.row_start + row_local * (uint32_t)P.row_stride;
+                // u = T(j/W), v = T((H-i)/H): quotient in Float64, rounded to Float32 (src/render.jl:26-27)
+                float su = (float)((double)(col + 1u) / (double)P.W);
+                float sv = (float)((double)((uint32_t)P.H - 1u - i0) / (double)P.H);
+                rng_begin(rng[r], i0 * (uint32_t)P.W + col, s0);
+                if (s0 != 0u) {  // first sample is centred (src/render.jl:30-36); du is drawn before dv
+                    su = su + __fdiv_rn(rng_f32(rng[r], k0, k1), (float)P.W);
+                    sv = sv + __fdiv_rn(rng_f32(rng[r], k0, k1), (float)P.H);
+                }
+                get_ray(P.cam, rng[r], k0, k1, su, sv, o[r], d[r]);
+                thr_r[r] = thr_g[r] = thr_b[r] = 1.0;
+                depth_left[r] = P.max_depth;
+                pix_local[r] = pl;
+                alive[r] = true;
+            }
+        }
+        bool any_alive = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) any_alive |= alive[r];
+        if (kMulti) {
+            if (__syncthreads_or(any_alive ? 1 : 0) == 0) break;  // also: everyone is done with both tile buffers
+        } else {
+            if (__ballot_sync(kFullMask, any_alive) == 0u) break;
+        }
+
+        // ------------------------------------------------------------ intersect: closest hit over the list
+        float best_t[R];
+        int best_k[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            best_t[r] = __int_as_float(0x7f800000);  // typemax(T) = Inf, src/ray_color.jl:19
+            best_k[r] = -1;
+        }
+        if (!kMulti) {
+            if (SWEEP == kSweepMask) sweep_tile_mask<R, kTraceBlock>(s_tile0, n, 0u, s_mask, o, d, alive, best_t, best_k);
+            else sweep_tile_branch<R>(s_tile0, n, 0u, o, d, alive, best_t, best_k);
+        } else {
+            if (threadIdx.x == 0) {  // prologue: tile 0 -> buffer 0
+                uint32_t cnt = n < kTileSpheres ? n : kTileSpheres;
+                mbar_arrive_expect_tx(&s_bar[0], cnt * 16u);
+                tma_bulk_g2s(s_tile0, P.geom, cnt * 16u, &s_bar[0]);
+            }
+            for (uint32_t t = 0; t < n_tiles; ++t) {
+                const uint32_t base = t * kTileSpheres;
+                const uint32_t cnt = n - base < kTileSpheres ? n - base : kTileSpheres;
+                if (threadIdx.x == 0 && t + 1u < n_tiles) {  // prefetch tile t+1 into the other buffer
+                    const uint32_t nb = base + kTileSpheres;
+                    const uint32_t ncnt = n - nb < kTileSpheres ? n - nb : kTileSpheres;
+                    unsigned long long* bar = &s_bar[(t + 1u) & 1u];
+                    mbar_arrive_expect_tx(bar, ncnt * 16u);
+                    tma_bulk_g2s((t & 1u) ? s_tile0 : s_tile1, P.geom + nb, ncnt * 16u, bar);
+                }
+                const float4* tile = (t & 1u) ? s_tile1 : s_tile0;
+                if (t & 1u) { mbar_wait(&s_bar[1], bar_phase1); bar_phase1 ^= 1u; }
+                else { mbar_wait(&s_bar[0], bar_phase0); bar_phase0 ^= 1u; }
+                if (SWEEP == kSweepMask) sweep_tile_mask<R, kTraceBlock>(tile, cnt, base, s_mask, o, d, alive, best_t, best_k);
+                else sweep_tile_branch<R>(tile, cnt, base, o, d, alive, best_t, best_k);
+                __syncthreads();  // the buffer may be overwritten by the prefetch issued in the next iteration
+            }
+        }
+
+        // ------------------------------------------------------------ shade / scatter / accumulate
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (!alive[r]) continue;
+            seg_count += 1;
+            bool finished = false;
+            double cr = 0.0, cg = 0.0, cb = 0.0;
+            if (best_k[r] < 0) {  // miss: sky (src/ray_color.jl:36)
+                double sr, sg, sb;
+                skycolor(d[r], sr, sg, sb);
+                cr = __dmul_rn(thr_r[r], sr);
+                cg = __dmul_rn(thr_g[r], sg);
+                cb = __dmul_rn(thr_b[r], sb);
+                finished = true;
+            } else if (--depth_left[r] == 0) {
+                finished = true;  // the next ray_color call returns black (src/ray_color.jl:15-17)
+            } else {
+                float4 g = __ldg(P.geom + best_k[r]);
+                float4 m = __ldg(P.mat + best_k[r]);
+                uint32_t kind = __ldg(P.kind + best_k[r]);
+                f3 att;
+                shade_hit(o[r], d[r], best_t[r], g, m, kind, rng[r], k0, k1, att);
+                thr_r[r] = __dmul_rn(thr_r[r], (double)att.x);
+                thr_g[r] = __dmul_rn(thr_g[r], (double)att.y);
+                thr_b[r] = __dmul_rn(thr_b[r], (double)att.z);
+            }
+            if (finished) {
+                // accumulate (src/render.jl:38): order-independent fixed-point atomics => the image is
+                // bit-identical for any schedule, rays-per-lane setting and GPU count
+                unsigned long long* a = P.accum + (unsigned long long)pix_local[r] * 4ull;
+                atomicAdd(a + 0, (unsigned long long)__double2ll_rn(cr * P.fx_scale));
+                atomicAdd(a + 1, (unsigned long long)__double2ll_rn(cg * P.fx_scale));
+                atomicAdd(a + 2, (unsigned long long)__double2ll_rn(cb * P.fx_scale));
+                alive[r] = false;
+            }
+        }
+    }
+    // ray-segment statistics: one atomic per warp
+    for (int off = 16; off > 0; off >>= 1) seg_count += __shfl_xor_sync(kFullMask, seg_count, off);
+    if (lane == 0 && seg_count) atomicAdd(P.counters + 1, (unsigned long long)seg_count);
+}
+
+// ---- resolve: accum / n_samples -> sqrt -> Float32 (src/render.jl:40, src/vec.jl:22) ------------------------
+__global__ void __launch_bounds__(256) resolve_kernel(const unsigned long long* __restrict__ accum, int W, int H,
+                                                      int n_rows, int row_start, int row_stride, int spp,
+                                                      double inv_scale, int column_major, float* __restrict__ out) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)n_rows * W;
+    if (t >= total) return;
+    int k, col;
+    if (column_major) { col = (int)(t / n_rows); k = (int)(t - (long long)col * n_rows); }
+    else { k = (int)(t / W); col = (int)(t - (long long)k * W); }
+    const unsigned long long* a = accum + ((long long)k * W + col) * 4;
+    float rgb[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double sum = (double)(long long)a[c] * inv_scale;
+        double lin = sum / (double)spp;
+        rgb[c] = (float)sqrt(lin);
+    }
+    long long at;
+    if (column_major) at = ((long long)col * H + (row_start + (long long)k * row_stride)) * 3;
+    else at = ((long long)k * W + col) * 3;
+    out[at + 0] = rgb[0];
+    out[at + 1] = rgb[1];
+    out[at + 2] = rgb[2];
+}
+
+// ---- assemble: tiles[g][k][col][3] (row i0 = g + k*G) -> Julia column-major image ---------------------------
+__global__ void __launch_bounds__(256) assemble_kernel(const float* __restrict__ tiles, int G, int W, int H,
+                                                       int rows_pad, float* __restrict__ out) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)W * H;
+    if (t >= total) return;
+    int col = (int)(t / H), i0 = (int)(t - (long long)col * H);
+    int g = i0 % G, k = i0 / G;
+    const float* src = tiles + (((long long)g * rows_pad + k) * W + col) * 3;
+    float* dst = out + t * 3;
+    dst[0] = src[0];
+    dst[1] = src[1];
+    dst[2] = src[2];
+}
+
+// ---- FP32 issue microbenchmarks ------------------------------------------------------------------------------
+constexpr int kPeakBlock = 256;
+constexpr int kPeakIters = 4096;
+constexpr int kPeakChains = 16;
+constexpr int kPeakSpheres = 512;
+constexpr int kPeakSweeps = 64;
+
+__global__ void __launch_bounds__(kPeakBlock) fp32_peak_ffma_kernel(float* out, float b, float c) {
+    float a[kPeakChains];
+#pragma unroll
+    for (int i = 0; i < kPeakChains; ++i) a[i] = (float)(threadIdx.x + i) * 1e-3f;
+    for (int it = 0; it < kPeakIters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kPeakChains; ++i) a[i] = fmaf(a[i], b, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kPeakChains; ++i) s += a[i];
+    if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // never true: keeps the chains alive
+}
+
+// the sweep's own instruction mix (mask variant: 11 FP32 + 1 SHF per test, 1 LDS.128 per R tests) with no
+// candidate ever resolved; ray data comes from memory so nothing is constant-folded
+template <int R>
+__global__ void __launch_bounds__(kPeakBlock) fp32_peak_sweep_kernel(float* out, const float* __restrict__ rays) {
+    __shared__ float4 s_geom[kPeakSpheres];
+    __shared__ uint32_t s_mask_peak[(kPeakSpheres / 32) * R * kPeakBlock];
+    for (int i = threadIdx.x; i < kPeakSpheres; i += blockDim.x)
+        s_geom[i] = make_float4(1000.f + (float)i, 2000.f, -3000.f, 0.5f);  // far off-axis: disc < 0 always
+    __syncthreads();
+    f3 o[R], d[R];
+    bool alive[R];
+    float best_t[R];
+    int best_k[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        o[r] = mk3(rays[0] + (float)threadIdx.x * 1e-3f, rays[1] + (float)r, rays[2]);
+        d[r] = mk3(rays[3], rays[4], rays[5]);
+        alive[r] = true;
+        best_t[r] = __int_as_float(0x7f800000);
+        best_k[r] = -1;
+    }
+    int hits = 0;
+    for (int it = 0; it < kPeakSweeps; ++it) {
+        sweep_tile_mask<R, kPeakBlock>(s_geom, kPeakSpheres, 0u, s_mask_peak + threadIdx.x, o, d, alive, best_t, best_k);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            hits += best_k[r] >= 0;
+            o[r].x += 1e-3f;
+        }
+    }
+    if (hits) out[blockIdx.x * blockDim.x + threadIdx.x] = (float)hits;
+}
+
+}  // namespace
+
+// ---- host launchers --------------------------------------------------------------------------------------------
+
+namespace {
+
+template <int R, int SWEEP, bool kMulti>
+cudaError_t launch_trace_variant(const TraceParams& p, int num_sms, int blocks_per_sm_override, cudaStream_t stream,
+                                 LaunchInfo* info) {
+    auto kern = fused_trace_kernel<R, SWEEP, kMulti>;
+    const uint32_t tile_cap = kMulti ? kTileSpheres : ((p.n_spheres + 31u) & ~31u);
+    const uint32_t chunks = tile_cap / 32u;
+    int smem = (int)((kMulti ? 2u : 1u) * tile_cap * 16u);
+    if (SWEEP == kSweepMask) smem += (int)(chunks * R * kTraceBlock * 4u);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTraceBlock, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    if (blocks_per_sm_override > 0 && blocks_per_sm_override < per_sm) per_sm = blocks_per_sm_override;
+    // persistent grid: every CTA is resident; never launch more lanes than there are paths
+    long long grid = (long long)num_sms * per_sm;
+    long long max_useful = (long long)((p.n_paths + (unsigned long long)(kTraceBlock * R) - 1ull) /
+                                       (unsigned long long)(kTraceBlock * R));
+    if (grid > max_useful) grid = max_useful;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, kTraceBlock, smem, stream>>>(p);
+    if (info) {
+        info->grid = (int)grid;
+        info->block = kTraceBlock;
+        info->smem_bytes = smem;
+        info->blocks_per_sm = per_sm;
+        info->launches = 1;
+        info->rays_per_lane = R;
+        info->sweep = SWEEP;
+    }
+    return cudaGetLastError();
+}
+
+template <int R, int SWEEP>
+cudaError_t launch_trace_tiles(const TraceParams& p, int num_sms, int bps, cudaStream_t stream, LaunchInfo* info) {
+    if (p.n_spheres <= kTileSpheres) return launch_trace_variant<R, SWEEP, false>(p, num_sms, bps, stream, info);
+    return launch_trace_variant<R, SWEEP, true>(p, num_sms, bps, stream, info);
+}
+
+template <int SWEEP>
+cudaError_t launch_trace_rays(const TraceParams& p, int num_sms, int bps, int R, cudaStream_t stream, LaunchInfo* info) {
+    switch (R) {
+        case 1: return launch_trace_tiles<1, SWEEP>(p, num_sms, bps, stream, info);
+        case 4: return launch_trace_tiles<4, SWEEP>(p, num_sms, bps, stream, info);
+        default: return launch_trace_tiles<2, SWEEP>(p, num_sms, bps, stream, info);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_fused_trace(const TraceParams& p, int num_sms, int blocks_per_sm_override, int rays_per_lane,
+                               int sweep, cudaStream_t stream, LaunchInfo* info) {
+    if (sweep == kSweepBranch) return launch_trace_rays<kSweepBranch>(p, num_sms, blocks_per_sm_override, rays_per_lane, stream, info);
+    return launch_trace_rays<kSweepMask>(p, num_sms, blocks_per_sm_override, rays_per_lane, stream, info);
+}
+
+cudaError_t launch_resolve(const unsigned long long* accum, int W, int H, int n_rows, int row_start, int row_stride,
+                           int spp, double inv_scale, int column_major, float* out, cudaStream_t stream) {
+    long long total = (long long)n_rows * W;
+    if (total <= 0) return cudaSuccess;
+    unsigned grid = (unsigned)((total + 255) / 256);
+    resolve_kernel<<<grid, 256, 0, stream>>>(accum, W, H, n_rows, row_start, row_stride, spp, inv_scale, column_major,
+                                             out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assemble(const float* tiles, int n_tiles, int W, int H, float* out, cudaStream_t stream) {
+    long long total = (long long)W * H;
+    if (total <= 0) return cudaSuccess;
+    int rows_pad = (H + n_tiles - 1) / n_tiles;
+    unsigned grid = (unsigned)((total + 255) / 256);
+    assemble_kernel<<<grid, 256, 0, stream>>>(tiles, n_tiles, W, H, rows_pad, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fp32_peak(int variant, int num_sms, float* scratch, cudaStream_t stream, double* fp32_instr) {
+    const int grid = num_sms * 8;
+    if (variant == 0) {
+        fp32_peak_ffma_kernel<<<grid, kPeakBlock, 0, stream>>>(scratch, 0.999f, 1e-4f);
+        *fp32_instr = (double)grid * kPeakBlock * (double)kPeakIters * kPeakChains;
+    } else {
+        // scratch[0..5] holds a ray (origin, direction) written by the caller
+        fp32_peak_sweep_kernel<2><<<grid, kPeakBlock, 0, stream>>>(scratch + 64, scratch);
+        *fp32_instr = (double)grid * kPeakBlock * 2.0 * (double)kPeakSweeps * kPeakSpheres * 11.0;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace rtw

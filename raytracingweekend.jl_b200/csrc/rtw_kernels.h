@@ -1,0 +1,49 @@
+// rtw_kernels.h -- host-visible launch interface of the sm_100a kernels (internal; the public ABI is include/rtw_b200.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rtw_device.cuh"
+
+namespace rtw {
+
+// HBM layout of one render on one device:
+//   geom   : n x float4 {cx,cy,cz,r}        (16 B aligned; staged to shared memory by 1-D bulk TMA, 1024-sphere tiles)
+//   mat    : n x float4 {albedo rgb, fuzz|ir}
+//   kind   : n x u32
+//   accum  : n_rows*W x 4 x i64  fixed-point radiance sums (r,g,b,pad), scale 2^fx_bits, order-independent atomics
+//   counters[0] = path ticket counter, counters[1] = ray segments traced
+struct TraceParams {
+    DevCamera cam;
+    const float4* geom;
+    const float4* mat;
+    const uint32_t* kind;
+    uint32_t n_spheres;
+    int W, H, spp, max_depth;
+    uint32_t key0, key1;  // Philox key = seed lo/hi
+    int row_start, row_stride, n_rows;
+    unsigned long long n_paths;  // n_rows * W * spp ; path ticket t -> pixel t / spp, sample t % spp
+    unsigned long long* accum;
+    double fx_scale;  // 2^fx_bits
+    unsigned long long* counters;
+};
+
+struct LaunchInfo {
+    int grid, block, smem_bytes, blocks_per_sm, launches, rays_per_lane, sweep;
+};
+
+constexpr int kSweepBranch = 1;  // RTW_SWEEP_BRANCH
+constexpr int kSweepMask = 2;    // RTW_SWEEP_MASK
+
+// spheres per shared-memory tile of the sweep (32 chunks of 32): 16 KB of geometry per buffer
+constexpr uint32_t kTileSpheres = 1024;
+
+cudaError_t launch_fused_trace(const TraceParams& p, int num_sms, int blocks_per_sm_override, int rays_per_lane,
+                               int sweep, cudaStream_t stream, LaunchInfo* info);
+cudaError_t launch_resolve(const unsigned long long* accum, int W, int H, int n_rows, int row_start, int row_stride,
+                           int spp, double inv_scale, int column_major, float* out, cudaStream_t stream);
+cudaError_t launch_assemble(const float* tiles, int n_tiles, int W, int H, float* out, cudaStream_t stream);
+// FP32 issue microbenchmarks; returns lane-instructions executed through *fp32_instr
+cudaError_t launch_fp32_peak(int variant, int num_sms, float* scratch, cudaStream_t stream, double* fp32_instr);
+
+}  // namespace rtw

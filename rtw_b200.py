@@ -1,0 +1,13 @@
+"""Import alias: the package directory is `raytracingweekend.jl_b200/` (a dot cannot appear in a Python
+module name), so `import rtw_b200` loads that directory as the package `rtw_b200`."""
+import importlib.util
+import sys
+from pathlib import Path
+
+_pkg_dir = Path(__file__).resolve().parent / "raytracingweekend.jl_b200"
+_spec = importlib.util.spec_from_file_location(
+    __name__, _pkg_dir / "__init__.py", submodule_search_locations=[str(_pkg_dir)]
+)
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

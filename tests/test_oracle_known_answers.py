@@ -1,0 +1,118 @@
+"""Pins the CPU oracle against every known answer the reference's own tests / notebook hold for the
+hot path.  CPU only."""
+import math
+
+import numpy as np
+import pytest
+
+
+def test_reflect_known_answer(oracle):
+    # test/runtests.jl:180 and src/pluto_RayTracingWeekend.jl:382 -- exact equality in Float64
+    out = oracle.reflect([0.6, -0.8, 0.0], [0.0, 1.0, 0.0])
+    assert out.tolist() == [0.6, 0.8, 0.0]
+
+
+def test_refract_known_answers(oracle):
+    # src/pluto_RayTracingWeekend.jl:603-615 (commented copy: test/runtests.jl:203-211)
+    d, n = [0.6, -0.8, 0.0], [0.0, 1.0, 0.0]
+    assert oracle.refract(d, n, 1.0).tolist() == [0.6, -0.8, 0.0]  # unchanged angle: exact ==
+    assert np.allclose(oracle.refract(d, n, 2.0), [0.87519, -0.483779, 0.0], atol=1e-3, rtol=0)  # wider
+    assert np.allclose(oracle.refract(d, n, 0.5), [0.3, -0.953939, 0.0], atol=1e-3, rtol=0)  # narrower
+    # the Float32 instantiation agrees with the Float64 one to Float32 precision
+    for ratio in (1.0, 2.0, 0.5):
+        assert np.allclose(oracle.refract(d, n, ratio, np.float32), oracle.refract(d, n, ratio), atol=1e-6)
+
+
+def test_near_zero_known_answer(oracle):
+    # test/runtests.jl:131  @test !near_zero(SA[0.4,0.5,0.1]);  src/vec.jl:20 threshold on the SQUARED length
+    assert not oracle.near_zero([0.4, 0.5, 0.1])
+    assert oracle.near_zero([1e-3, 1e-3, 1e-3])  # 3e-6 < 1e-5
+    assert not oracle.near_zero([3e-3, 1e-3, 1e-3])  # 1.1e-5
+    assert oracle.near_zero([1e-3, 1e-3, 1e-3], np.float32)
+
+
+def test_hit_sphere_matches_hit_sphere2_closed_form(oracle):
+    # test/runtests.jl:99-111: t = (-b - sqrt(b^2 - 4ac)) / 2a with b = 2 oc.d, a = 1
+    rng = np.random.default_rng(7)
+    center, radius = np.array([0.0, 0.0, -1.0]), 0.5
+    hits = 0
+    for _ in range(500):
+        d = rng.normal(size=3) * [0.3, 0.3, 1.0]
+        d[2] = -abs(d[2])
+        d /= np.linalg.norm(d)
+        o = rng.normal(size=3) * 0.05
+        oc = o - center
+        b = 2 * oc.dot(d)
+        c = oc.dot(oc) - radius ** 2
+        disc = b * b - 4 * c
+        got = oracle.hit_sphere(center, radius, o, d, 1e-4, math.inf)
+        if disc < 0:
+            assert got is None
+            continue
+        t_ref = (-b - math.sqrt(disc)) / 2
+        if t_ref < 1e-4:
+            continue
+        hits += 1
+        t, p, n, front = got
+        assert t == pytest.approx(t_ref, rel=1e-12, abs=1e-12)
+        assert np.allclose(p, o + t * d, atol=1e-12)
+        assert np.allclose(n, (p - center) / radius, atol=1e-12) and front
+    assert hits > 100
+
+
+def test_hit_sphere_far_root_inside_and_negative_radius(oracle):
+    # src/hit.jl:23-29: origin inside the sphere => near root < tmin => far root; front_face False, normal flipped
+    t, p, n, front = oracle.hit_sphere([0, 0, 0], 1.0, [0, 0, 0], [0, 0, -1], 1e-4, math.inf)
+    assert t == 1.0 and not front and n.tolist() == [0.0, 0.0, 1.0]
+    # negative radius (hollow glass, src/scenes.jl:35-36) flips the outward normal via the division (src/hit.jl:33)
+    t, p, n, front = oracle.hit_sphere([0, 0, -2], -0.5, [0, 0, 0], [0, 0, -1], 1e-4, math.inf)
+    assert t == 1.5 and not front and n.tolist() == [0.0, 0.0, 1.0]
+    # tmax is inclusive (src/hit.jl:24: `tmax < root` rejects) -- a later sphere at the same t wins (src/hit.jl:44-46)
+    assert oracle.hit_sphere([0, 0, -2], 0.5, [0, 0, 0], [0, 0, -1], 1e-4, 1.5) is not None
+    assert oracle.hit_sphere([0, 0, -2], 0.5, [0, 0, 0], [0, 0, -1], 1e-4, 1.4999) is None
+    # behind the ray
+    assert oracle.hit_sphere([0, 0, 2], 0.5, [0, 0, 0], [0, 0, -1], 1e-4, math.inf) is None
+
+
+def test_skycolor_closed_form(oracle):
+    # src/ray_color.jl:1-6: (1-t)*white + t*skyblue with t = 0.5*(dir.y+1)
+    assert np.allclose(oracle.skycolor([0, 1, 0]), [0.5, 0.7, 1.0])
+    assert np.allclose(oracle.skycolor([0, -1, 0]), [1.0, 1.0, 1.0])
+    assert np.allclose(oracle.skycolor([1, 0, 0]), [0.75, 0.85, 1.0])
+
+
+def test_reflectance_schlick(oracle):
+    # src/light.jl:19-25: r0 + (1-r0)(1-cos)^5, r0 = ((1-q)/(1+q))^2
+    for cos_t, q in [(1.0, 1.5), (0.0, 1.5), (0.3, 1 / 1.5), (0.9, 0.7)]:
+        r0 = ((1 - q) / (1 + q)) ** 2
+        assert oracle.reflectance(cos_t, q) == pytest.approx(r0 + (1 - r0) * (1 - cos_t) ** 5, rel=1e-12)
+        assert oracle.reflectance(cos_t, q, np.float32) == pytest.approx(r0 + (1 - r0) * (1 - cos_t) ** 5, rel=1e-5)
+
+
+def test_philox_known_answer_vectors(oracle):
+    # Random123 kat_vectors for philox4x32-10
+    assert oracle.philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert oracle.philox4x32_10([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert oracle.philox4x32_10([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == [
+        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_path_stream_layout(oracle):
+    # k-th uniform = word (k mod 4) of block (k div 4); counter = (block, sample, pixel, "RTW1"); f32 = (w>>9)*2^-23
+    seed, pixel, sample = 0x1234567800000001, 4321, 17
+    got = oracle.path_stream(seed, pixel, sample, 12)
+    key = [seed & 0xFFFFFFFF, seed >> 32]
+    exp = []
+    for blk in range(3):
+        exp += [np.float32(w >> 9) * np.float32(2.0 ** -23) for w in oracle.philox4x32_10([blk, sample, pixel, 0x52545731], key)]
+    assert got.tolist() == [float(x) for x in exp]
+    assert got.min() >= 0.0 and got.max() < 1.0
+
+
+def test_xoroshiro_matches_host_mirror(oracle, rtw):
+    # two independent restatements (C and Python) of the published algorithm agree; NOT verified against Julia
+    for seed in (1, 2, 16):
+        g = rtw.Xoroshiro128Plus(seed)
+        assert [g.next_u64() for _ in range(64)] == [int(x) for x in oracle.xoroshiro_u64(seed, 64)]
+        g = rtw.Xoroshiro128Plus(seed)
+        assert [float(g.rand(np.float32)) for _ in range(64)] == oracle.xoroshiro_f32(seed, 64).tolist()

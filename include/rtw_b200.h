@@ -95,6 +95,7 @@ typedef struct rtw_ctx rtw_ctx;
 #define RTW_SWEEP_DEFAULT 0       /* library default (the fastest measured)                           */
 #define RTW_SWEEP_BRANCH 1        /* test + immediate root selection under a branch                    */
 #define RTW_SWEEP_MASK 2          /* sign-bit candidate masks, roots resolved after the sweep          */
+#define RTW_SWEEP_PACKED 3        /* RTW_SWEEP_MASK on packed FP32x2 instructions (two spheres / instr) */
 
 #define RTW_MODE_FUSED 0          /* one persistent kernel: raygen -> {intersect, shade} loop -> accumulate */
 #define RTW_MODE_WAVEFRONT 1      /* separate raygen / intersect / shade / accumulate kernels + compaction  */
@@ -181,7 +182,8 @@ RTW_API int rtw_assemble_tiles_device(rtw_ctx* ctx, int device_slot, const float
 
 /*
  * FP32 issue microbenchmark on device `device_slot`: independent FFMA chains on every SM.
- *   variant 0: pure FFMA;  variant 1: the sweep's own mix per sphere test (3 FADD, 2 FMUL, 6 FFMA, 1 FSETP, 1 LDS.128)
+ *   variant 0: pure FFMA;  variant 1: the scalar mask sweep's own mix (3 FADD, 2 FMUL, 6 FFMA + 1 SHF, 1 LDS.128 per test);
+ *   variant 2: the packed FP32x2 mask sweep (the same 11 lane-ops per test, two tests per instruction)
  * Writes achieved FP32 instructions/s (lane-instructions, i.e. warp instructions x 32) and the kernel time.
  */
 RTW_API int rtw_measure_fp32_peak(rtw_ctx* ctx, int device_slot, int variant, double* fp32_instr_per_s, float* ms);

@@ -12,6 +12,7 @@ The directory name contains a dot, so import it through the repo-root alias modu
 from ._lib import (EXPORTED_SYMBOLS, LIB_PATH, RTW_MODE_FUSED, RTW_MODE_WAVEFRONT, RTW_OPT_BLOCKS_PER_SM,
                    RTW_OPT_COLLECT_TIMING, RTW_OPT_MODE, RTW_OPT_RAYS_PER_LANE, RTW_OPT_STRIP, RTW_OPT_SWEEP,
                    RtwError, rtw_camera, rtw_stats)
+from . import sharding
 from .api import DEFAULT_MAX_DEPTH, DEFAULT_SEED, Renderer, render
 from .host import (TRNG, Camera, Dielectric, HittableList, Lambertian, Metal, Sphere, Vec3, Xoroshiro128Plus,
                    default_camera, flatten_scene, image_height, near_zero, random_between, reseed,
@@ -23,5 +24,5 @@ __all__ = [
     "Sphere", "HittableList", "Lambertian", "Metal", "Dielectric", "Camera", "default_camera", "render", "Renderer",
     "scene_2_spheres", "scene_4_spheres", "scene_blue_red_spheres", "scene_diel_spheres", "scene_random_spheres",
     "flatten_scene", "image_height", "t_default_cam", "t_cam1", "t_cam2", "RtwError", "rtw_camera", "rtw_stats",
-    "EXPORTED_SYMBOLS", "LIB_PATH", "DEFAULT_MAX_DEPTH", "DEFAULT_SEED",
+    "EXPORTED_SYMBOLS", "LIB_PATH", "DEFAULT_MAX_DEPTH", "DEFAULT_SEED", "sharding",
 ]

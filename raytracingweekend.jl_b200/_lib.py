@@ -44,6 +44,11 @@ RTW_OPT_COLLECT_TIMING = 4
 RTW_OPT_RAYS_PER_LANE = 5
 RTW_OPT_SWEEP = 6
 
+RTW_SWEEP_DEFAULT = 0
+RTW_SWEEP_BRANCH = 1
+RTW_SWEEP_MASK = 2
+RTW_SWEEP_PACKED = 3
+
 RTW_MODE_FUSED = 0
 RTW_MODE_WAVEFRONT = 1
 

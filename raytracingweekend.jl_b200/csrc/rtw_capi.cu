@@ -23,6 +23,7 @@ struct DeviceState {
     cudaEvent_t ev_tile = nullptr;  // tile ready (multi-device gather)
     // scene
     float4* d_geom = nullptr;
+    float4* d_geom_pairs = nullptr;
     float4* d_mat = nullptr;
     uint32_t* d_kind = nullptr;
     size_t scene_cap = 0;
@@ -62,8 +63,8 @@ struct rtw_ctx {
 namespace {
 
 // defaults chosen by measurement on B200 (profiles/): see DESIGN.md "Kernel variants"
-constexpr int kDefaultRaysPerLane = 2;
-constexpr int kDefaultSweep = RTW_SWEEP_MASK;
+constexpr int kDefaultRaysPerLane = 1;
+constexpr int kDefaultSweep = RTW_SWEEP_PACKED;
 
 int fail(rtw_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg;
@@ -160,6 +161,7 @@ int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, in
         rtw::TraceParams p;
         p.cam = to_dev_camera(cam);
         p.geom = ds.d_geom;
+        p.geom_pairs = ds.d_geom_pairs;
         p.mat = ds.d_mat;
         p.kind = ds.d_kind;
         p.n_spheres = ctx->n_spheres;
@@ -207,21 +209,33 @@ int set_scene_locked(rtw_ctx* ctx, const float* geom4, const float* mat4, const 
     if (n > (1u << 26)) return fail(ctx, RTW_E_INVALID_ARG, "too many spheres");
     for (uint32_t i = 0; i < n; ++i)
         if (kind[i] > RTW_DIELECTRIC) return fail(ctx, RTW_E_UNSUPPORTED, "unknown material kind (only Lambertian/Metal/Dielectric)");
+    // pair layout of the geometry for the packed sweep: spheres (2p, 2p+1) -> {xa,xb,ya,yb}{za,zb,ra,rb}
+    std::vector<float> pairs((size_t)((n + 1u) / 2u) * 8u, 0.0f);
+    for (uint32_t i = 0; i < n; ++i) {
+        float* dst = pairs.data() + (size_t)(i >> 1) * 8u + (i & 1u);
+        dst[0] = geom4[4 * (size_t)i + 0];
+        dst[2] = geom4[4 * (size_t)i + 1];
+        dst[4] = geom4[4 * (size_t)i + 2];
+        dst[6] = geom4[4 * (size_t)i + 3];
+    }
     for (auto& ds : ctx->dev) {
         RTW_CUDA(ctx, cudaSetDevice(ds.device));
         if (n > ds.scene_cap || !ds.d_geom) {
             if (ds.d_geom) cudaFree(ds.d_geom);
+            if (ds.d_geom_pairs) cudaFree(ds.d_geom_pairs);
             if (ds.d_mat) cudaFree(ds.d_mat);
             if (ds.d_kind) cudaFree(ds.d_kind);
-            ds.d_geom = nullptr; ds.d_mat = nullptr; ds.d_kind = nullptr; ds.scene_cap = 0;
+            ds.d_geom = nullptr; ds.d_geom_pairs = nullptr; ds.d_mat = nullptr; ds.d_kind = nullptr; ds.scene_cap = 0;
             size_t cap = n ? n : 1;
             RTW_CUDA(ctx, cudaMalloc((void**)&ds.d_geom, cap * sizeof(float4)));
+            RTW_CUDA(ctx, cudaMalloc((void**)&ds.d_geom_pairs, (cap + 1) * sizeof(float4)));
             RTW_CUDA(ctx, cudaMalloc((void**)&ds.d_mat, cap * sizeof(float4)));
             RTW_CUDA(ctx, cudaMalloc((void**)&ds.d_kind, cap * sizeof(uint32_t)));
             ds.scene_cap = cap;
         }
         if (n) {
             RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_geom, geom4, (size_t)n * 16, cudaMemcpyHostToDevice, ds.stream));
+            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_geom_pairs, pairs.data(), pairs.size() * sizeof(float), cudaMemcpyHostToDevice, ds.stream));
             RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_mat, mat4, (size_t)n * 16, cudaMemcpyHostToDevice, ds.stream));
             RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_kind, kind, (size_t)n * 4, cudaMemcpyHostToDevice, ds.stream));
         }
@@ -402,7 +416,7 @@ int rtw_destroy(rtw_ctx* ctx) {
     for (auto& ds : ctx->dev) {
         if (cudaSetDevice(ds.device) != cudaSuccess) continue;
         if (ds.stream) cudaStreamSynchronize(ds.stream);
-        cudaFree(ds.d_geom); cudaFree(ds.d_mat); cudaFree(ds.d_kind);
+        cudaFree(ds.d_geom); cudaFree(ds.d_geom_pairs); cudaFree(ds.d_mat); cudaFree(ds.d_kind);
         cudaFree(ds.d_accum); cudaFree(ds.d_counters); cudaFree(ds.d_tile);
         cudaFree(ds.d_gather); cudaFree(ds.d_image); cudaFree(ds.d_scratch);
         if (ds.h_counters) cudaFreeHost(ds.h_counters);
@@ -433,7 +447,7 @@ int rtw_set_option(rtw_ctx* ctx, int option, int64_t value) {
             ctx->rays_per_lane = (int)value;
             return RTW_OK;
         case RTW_OPT_SWEEP:
-            if (value < 0 || value > RTW_SWEEP_MASK) return fail(ctx, RTW_E_INVALID_ARG, "unknown sweep variant");
+            if (value < 0 || value > RTW_SWEEP_PACKED) return fail(ctx, RTW_E_INVALID_ARG, "unknown sweep variant");
             ctx->sweep = (int)value;
             return RTW_OK;
         case RTW_OPT_BLOCKS_PER_SM:
@@ -539,7 +553,7 @@ int rtw_measure_fp32_peak(rtw_ctx* ctx, int device_slot, int variant, double* fp
     if (!ctx || !fp32_instr_per_s) return RTW_E_INVALID_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (device_slot < 0 || device_slot >= (int)ctx->dev.size()) return fail(ctx, RTW_E_INVALID_ARG, "bad device_slot");
-    if (variant < 0 || variant > 1) return fail(ctx, RTW_E_INVALID_ARG, "variant must be 0 or 1");
+    if (variant < 0 || variant > 2) return fail(ctx, RTW_E_INVALID_ARG, "variant must be 0, 1 or 2");
     DeviceState& ds = ctx->dev[device_slot];
     RTW_CUDA(ctx, cudaSetDevice(ds.device));
     double instr = 0.0, best = 0.0;

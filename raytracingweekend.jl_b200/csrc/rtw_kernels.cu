@@ -136,6 +136,86 @@ __device__ __forceinline__ void sweep_tile_mask(const float4* __restrict__ tile,
     }
 }
 
+// RTW_SWEEP_PACKED: the mask sweep on Blackwell's packed FP32x2 pipe.  Two spheres are tested per instruction
+// (FADD2/FMUL2/FFMA2, IEEE rn per half => bit-identical to the scalar form); the ray components are broadcast
+// operands.  A packed instruction keeps the FP32 pipe busy for two cycles but takes one issue slot, so the
+// LDS.128 / funnel-shift / loop instructions issue in the shadow of the arithmetic: the loop is bound by the
+// FP32 pipe (11 lane-ops per test), not by instruction issue.
+// Shared-memory layout ("pair layout"): for spheres (a,b) = (2p, 2p+1): {xa,xb,ya,yb} {za,zb,ra,rb}.
+__device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 neg2(float a, float b) { return make_float2(-a, -b); }
+
+__device__ __forceinline__ float4 pair_layout_fetch(const float4* __restrict__ tile, uint32_t kl) {
+    const float* f = reinterpret_cast<const float*>(tile + (kl >> 1) * 2u) + (kl & 1u);
+    return make_float4(f[0], f[2], f[4], f[6]);
+}
+
+template <int R, int kBlock>
+__device__ __forceinline__ void sweep_tile_packed(const float4* __restrict__ tile, uint32_t count, uint32_t k_base,
+                                                  uint32_t* __restrict__ s_mask, const f3 (&o)[R], const f3 (&d)[R],
+                                                  const bool (&alive)[R], float (&best_t)[R], int (&best_k)[R]) {
+    const float tmin = 1e-4f;
+    const uint32_t nchunks = (count + 31u) >> 5;
+    uint32_t summary[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) summary[r] = 0u;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const float4* ch = tile + c * 32u;  // 16 pairs x 2 float4
+        uint32_t m[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) m[r] = 0u;
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            const float4 A = ch[2 * p], B = ch[2 * p + 1];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                // oc = o - c (src/hit.jl:13) for both spheres of the pair
+                const float2 ocx = __fadd2_rn(dup2(o[r].x), neg2(A.x, A.y));
+                const float2 ocy = __fadd2_rn(dup2(o[r].y), neg2(A.z, A.w));
+                const float2 ocz = __fadd2_rn(dup2(o[r].z), neg2(B.x, B.y));
+                // half_b = oc . d (src/hit.jl:16), dot = fma(z,z, fma(y,y, x*x))
+                const float2 hb = __ffma2_rn(ocz, dup2(d[r].z), __ffma2_rn(ocy, dup2(d[r].y), __fmul2_rn(ocx, dup2(d[r].x))));
+                // c = oc . oc - radius^2 (src/hit.jl:17)
+                const float2 q = __ffma2_rn(ocz, ocz, __ffma2_rn(ocy, ocy, __fmul2_rn(ocx, ocx)));
+                const float2 rr = make_float2(B.z, B.w);
+                const float2 cq = __ffma2_rn(neg2(rr.x, rr.y), rr, q);
+                // discriminant = half_b^2 - c (src/hit.jl:18)
+                const float2 disc = __ffma2_rn(hb, hb, neg2(cq.x, cq.y));
+                m[r] = __funnelshift_l(__float_as_uint(disc.x), m[r], 1);
+                m[r] = __funnelshift_l(__float_as_uint(disc.y), m[r], 1);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            s_mask[(c * R + r) * kBlock] = m[r];
+            summary[r] |= (m[r] != 0xffffffffu ? 1u : 0u) << c;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (!alive[r]) continue;
+        uint32_t sum = summary[r], cand = 0u, c = 0u;
+        for (;;) {
+            if (cand == 0u) {
+                if (sum == 0u) break;
+                c = (uint32_t)__ffs((int)sum) - 1u;
+                sum &= sum - 1u;
+                cand = ~s_mask[(c * R + r) * kBlock];
+                uint32_t valid = count - c * 32u;
+                if (valid < 32u) cand &= 0xffffffffu << (32u - valid);
+                if (cand == 0u) continue;
+            }
+            uint32_t j = (uint32_t)__clz((int)cand);
+            cand &= ~(0x80000000u >> j);
+            uint32_t kl = c * 32u + j;
+            float4 s = pair_layout_fetch(tile, kl);
+            float hb;
+            float disc = sphere_disc(s, o[r], d[r], hb);  // scalar redo: bit-identical to the packed value
+            if (sphere_accept(disc, hb, tmin, best_t[r])) best_k[r] = (int)(k_base + kl);
+        }
+    }
+}
+
 // ---- the persistent fused kernel ------------------------------------------------------------------------------
 // kMulti = false: the whole list (<= kTileSpheres) is staged once; warps then run free of CTA barriers.
 // kMulti = true : the list is streamed per bounce through two 16 KB TMA buffers, CTA-synchronously.
@@ -145,6 +225,9 @@ __global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_bar[2];
     const uint32_t n = P.n_spheres;
+    // the packed sweep stages the pair layout (even sphere count, zero padded); the others the plain AoS list
+    const float4* __restrict__ g_src = SWEEP == kSweepPacked ? P.geom_pairs : P.geom;
+    const uint32_t n_stage = SWEEP == kSweepPacked ? ((n + 1u) & ~1u) : n;  // spheres worth of bytes to copy
     const uint32_t n_tiles = kMulti ? (n + kTileSpheres - 1u) / kTileSpheres : 1u;
     const uint32_t tile_cap = kMulti ? kTileSpheres : ((n + 31u) & ~31u);  // spheres per buffer (multiple of 32)
     float4* s_tile0 = reinterpret_cast<float4*>(smem_raw);
@@ -165,8 +248,8 @@ __global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
     uint32_t bar_phase0 = 0u, bar_phase1 = 0u;
     if (!kMulti) {
         if (threadIdx.x == 0 && n > 0u) {
-            mbar_arrive_expect_tx(&s_bar[0], n * 16u);
-            tma_bulk_g2s(s_tile0, P.geom, n * 16u, &s_bar[0]);
+            mbar_arrive_expect_tx(&s_bar[0], n_stage * 16u);
+            tma_bulk_g2s(s_tile0, g_src, n_stage * 16u, &s_bar[0]);
         }
         if (n > 0u) mbar_wait(&s_bar[0], 0u);
     }
@@ -274,28 +357,30 @@ __global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
             best_k[r] = -1;
         }
         if (!kMulti) {
-            if (SWEEP == kSweepMask) sweep_tile_mask<R, kTraceBlock>(s_tile0, n, 0u, s_mask, o, d, alive, best_t, best_k);
+            if (SWEEP == kSweepPacked) sweep_tile_packed<R, kTraceBlock>(s_tile0, n, 0u, s_mask, o, d, alive, best_t, best_k);
+            else if (SWEEP == kSweepMask) sweep_tile_mask<R, kTraceBlock>(s_tile0, n, 0u, s_mask, o, d, alive, best_t, best_k);
             else sweep_tile_branch<R>(s_tile0, n, 0u, o, d, alive, best_t, best_k);
         } else {
             if (threadIdx.x == 0) {  // prologue: tile 0 -> buffer 0
-                uint32_t cnt = n < kTileSpheres ? n : kTileSpheres;
+                uint32_t cnt = n_stage < kTileSpheres ? n_stage : kTileSpheres;
                 mbar_arrive_expect_tx(&s_bar[0], cnt * 16u);
-                tma_bulk_g2s(s_tile0, P.geom, cnt * 16u, &s_bar[0]);
+                tma_bulk_g2s(s_tile0, g_src, cnt * 16u, &s_bar[0]);
             }
             for (uint32_t t = 0; t < n_tiles; ++t) {
                 const uint32_t base = t * kTileSpheres;
                 const uint32_t cnt = n - base < kTileSpheres ? n - base : kTileSpheres;
                 if (threadIdx.x == 0 && t + 1u < n_tiles) {  // prefetch tile t+1 into the other buffer
                     const uint32_t nb = base + kTileSpheres;
-                    const uint32_t ncnt = n - nb < kTileSpheres ? n - nb : kTileSpheres;
+                    const uint32_t ncnt = n_stage - nb < kTileSpheres ? n_stage - nb : kTileSpheres;
                     unsigned long long* bar = &s_bar[(t + 1u) & 1u];
                     mbar_arrive_expect_tx(bar, ncnt * 16u);
-                    tma_bulk_g2s((t & 1u) ? s_tile0 : s_tile1, P.geom + nb, ncnt * 16u, bar);
+                    tma_bulk_g2s((t & 1u) ? s_tile0 : s_tile1, g_src + nb, ncnt * 16u, bar);
                 }
                 const float4* tile = (t & 1u) ? s_tile1 : s_tile0;
                 if (t & 1u) { mbar_wait(&s_bar[1], bar_phase1); bar_phase1 ^= 1u; }
                 else { mbar_wait(&s_bar[0], bar_phase0); bar_phase0 ^= 1u; }
-                if (SWEEP == kSweepMask) sweep_tile_mask<R, kTraceBlock>(tile, cnt, base, s_mask, o, d, alive, best_t, best_k);
+                if (SWEEP == kSweepPacked) sweep_tile_packed<R, kTraceBlock>(tile, cnt, base, s_mask, o, d, alive, best_t, best_k);
+                else if (SWEEP == kSweepMask) sweep_tile_mask<R, kTraceBlock>(tile, cnt, base, s_mask, o, d, alive, best_t, best_k);
                 else sweep_tile_branch<R>(tile, cnt, base, o, d, alive, best_t, best_k);
                 __syncthreads();  // the buffer may be overwritten by the prefetch issued in the next iteration
             }
@@ -407,12 +492,13 @@ __global__ void __launch_bounds__(kPeakBlock) fp32_peak_ffma_kernel(float* out, 
 
 // the sweep's own instruction mix (mask variant: 11 FP32 + 1 SHF per test, 1 LDS.128 per R tests) with no
 // candidate ever resolved; ray data comes from memory so nothing is constant-folded
-template <int R>
+template <int R, bool kPacked>
 __global__ void __launch_bounds__(kPeakBlock) fp32_peak_sweep_kernel(float* out, const float* __restrict__ rays) {
     __shared__ float4 s_geom[kPeakSpheres];
     __shared__ uint32_t s_mask_peak[(kPeakSpheres / 32) * R * kPeakBlock];
     for (int i = threadIdx.x; i < kPeakSpheres; i += blockDim.x)
-        s_geom[i] = make_float4(1000.f + (float)i, 2000.f, -3000.f, 0.5f);  // far off-axis: disc < 0 always
+        s_geom[i] = kPacked ? ((i & 1) ? make_float4(-3000.f, -3000.f, 0.5f, 0.5f) : make_float4(1000.f + (float)i, 1001.f + (float)i, 2000.f, 2000.f))
+                            : make_float4(1000.f + (float)i, 2000.f, -3000.f, 0.5f);  // far off-axis: disc < 0 always
     __syncthreads();
     f3 o[R], d[R];
     bool alive[R];
@@ -428,7 +514,8 @@ __global__ void __launch_bounds__(kPeakBlock) fp32_peak_sweep_kernel(float* out,
     }
     int hits = 0;
     for (int it = 0; it < kPeakSweeps; ++it) {
-        sweep_tile_mask<R, kPeakBlock>(s_geom, kPeakSpheres, 0u, s_mask_peak + threadIdx.x, o, d, alive, best_t, best_k);
+        if (kPacked) sweep_tile_packed<R, kPeakBlock>(s_geom, kPeakSpheres, 0u, s_mask_peak + threadIdx.x, o, d, alive, best_t, best_k);
+        else sweep_tile_mask<R, kPeakBlock>(s_geom, kPeakSpheres, 0u, s_mask_peak + threadIdx.x, o, d, alive, best_t, best_k);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             hits += best_k[r] >= 0;
@@ -451,7 +538,7 @@ cudaError_t launch_trace_variant(const TraceParams& p, int num_sms, int blocks_p
     const uint32_t tile_cap = kMulti ? kTileSpheres : ((p.n_spheres + 31u) & ~31u);
     const uint32_t chunks = tile_cap / 32u;
     int smem = (int)((kMulti ? 2u : 1u) * tile_cap * 16u);
-    if (SWEEP == kSweepMask) smem += (int)(chunks * R * kTraceBlock * 4u);
+    if (SWEEP != kSweepBranch) smem += (int)(chunks * R * kTraceBlock * 4u);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -498,7 +585,8 @@ cudaError_t launch_trace_rays(const TraceParams& p, int num_sms, int bps, int R,
 cudaError_t launch_fused_trace(const TraceParams& p, int num_sms, int blocks_per_sm_override, int rays_per_lane,
                                int sweep, cudaStream_t stream, LaunchInfo* info) {
     if (sweep == kSweepBranch) return launch_trace_rays<kSweepBranch>(p, num_sms, blocks_per_sm_override, rays_per_lane, stream, info);
-    return launch_trace_rays<kSweepMask>(p, num_sms, blocks_per_sm_override, rays_per_lane, stream, info);
+    if (sweep == kSweepMask) return launch_trace_rays<kSweepMask>(p, num_sms, blocks_per_sm_override, rays_per_lane, stream, info);
+    return launch_trace_rays<kSweepPacked>(p, num_sms, blocks_per_sm_override, rays_per_lane, stream, info);
 }
 
 cudaError_t launch_resolve(const unsigned long long* accum, int W, int H, int n_rows, int row_start, int row_stride,
@@ -527,8 +615,9 @@ cudaError_t launch_fp32_peak(int variant, int num_sms, float* scratch, cudaStrea
         *fp32_instr = (double)grid * kPeakBlock * (double)kPeakIters * kPeakChains;
     } else {
         // scratch[0..5] holds a ray (origin, direction) written by the caller
-        fp32_peak_sweep_kernel<2><<<grid, kPeakBlock, 0, stream>>>(scratch + 64, scratch);
-        *fp32_instr = (double)grid * kPeakBlock * 2.0 * (double)kPeakSweeps * kPeakSpheres * 11.0;
+        if (variant == 1) fp32_peak_sweep_kernel<1, false><<<grid, kPeakBlock, 0, stream>>>(scratch + 64, scratch);
+        else fp32_peak_sweep_kernel<1, true><<<grid, kPeakBlock, 0, stream>>>(scratch + 64, scratch);
+        *fp32_instr = (double)grid * kPeakBlock * 1.0 * (double)kPeakSweeps * kPeakSpheres * 11.0;
     }
     return cudaGetLastError();
 }

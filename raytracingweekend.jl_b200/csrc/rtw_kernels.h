@@ -16,6 +16,7 @@ namespace rtw {
 struct TraceParams {
     DevCamera cam;
     const float4* geom;
+    const float4* geom_pairs;  // pair layout for the packed sweep: {xa,xb,ya,yb}{za,zb,ra,rb} per 2 spheres
     const float4* mat;
     const uint32_t* kind;
     uint32_t n_spheres;
@@ -34,6 +35,7 @@ struct LaunchInfo {
 
 constexpr int kSweepBranch = 1;  // RTW_SWEEP_BRANCH
 constexpr int kSweepMask = 2;    // RTW_SWEEP_MASK
+constexpr int kSweepPacked = 3;  // RTW_SWEEP_PACKED
 
 // spheres per shared-memory tile of the sweep (32 chunks of 32): 16 KB of geometry per buffer
 constexpr uint32_t kTileSpheres = 1024;

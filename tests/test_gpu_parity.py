@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3  # per-channel L-infinity, Float32 image after gamma (north_star)
 
 
-def _compare(img_gpu, img_cpu, max_mismatch_frac=1e-4):
+def _compare(img_gpu, img_cpu, max_mismatch_frac=1e-3):
     assert img_gpu.shape == img_cpu.shape and img_gpu.dtype == np.float32
     diff = np.abs(img_gpu.astype(np.float64) - img_cpu.astype(np.float64))
     linf = float(diff.max()) if diff.size else 0.0
@@ -21,11 +21,11 @@ def _compare(img_gpu, img_cpu, max_mismatch_frac=1e-4):
     n_diff = int((img_gpu != img_cpu).sum())
     assert linf <= TOL and n_bad == 0, f"Linf={linf}, values over tol={n_bad}"
     # bit-level: a handful of 1-ulp differences at most (Float64 sum order), never a diverged path
-    assert n_diff <= max(2, int(max_mismatch_frac * img_cpu.size)), f"{n_diff} of {img_cpu.size} values differ (Linf={linf})"
+    assert n_diff <= max(8, int(max_mismatch_frac * img_cpu.size)) and linf < 1e-6, f"{n_diff} of {img_cpu.size} values differ (Linf={linf})"
     return linf, n_diff
 
 
-@pytest.mark.parametrize("rays,sweep", [(1, 1), (2, 1), (1, 2), (2, 2), (4, 2)])
+@pytest.mark.parametrize("rays,sweep", [(1, 1), (2, 1), (1, 2), (2, 2), (4, 2), (1, 3), (2, 3), (4, 3)])
 def test_cfg1_scene_2_spheres_all_variants(rtw, oracle, renderer, scenes, rays, sweep):
     # BASELINE configs[0]: scene_2_spheres, 96x54, 16 spp, 4 bounces, Float32 (test/runtests.jl:194 shape)
     g, m, k = scenes["two"]
@@ -126,7 +126,7 @@ def test_large_list_streams_through_tma_tiles(rtw, oracle, renderer):
     scene = rtw.flatten_scene(rtw.scene_random_spheres(half_extent=26))  # ~2700 spheres, ragged last tile
     assert len(scene[2]) > 2 * 1024 and len(scene[2]) % 1024 != 0
     cam = rtw.t_cam1()
-    for rays, sweep in [(2, 2), (1, 1)]:
+    for rays, sweep in [(1, 3), (2, 3), (2, 2), (1, 1)]:
         renderer.set_option(rtw.RTW_OPT_RAYS_PER_LANE, rays)
         renderer.set_option(rtw.RTW_OPT_SWEEP, sweep)
         try:
@@ -196,4 +196,4 @@ def test_full_size_properties_without_oracle(rtw, renderer, scenes):
     assert st["paths"] == 1920 * 1080 * 2 and st["paths"] <= st["ray_segments"] <= 50 * st["paths"]
     assert st["sphere_tests"] == st["ray_segments"] * len(scenes["random"][2])
     # sky region (top-left corner) is smooth and bluish-white; ground region is darker
-    assert a[:40, :40].std() < 0.05 and a[:40, :40, 2].mean() > 0.9
+    assert a[:40, :40].std(axis=(0, 1)).max() < 0.02 and a[:40, :40, 2].mean() > 0.9

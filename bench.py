@@ -196,7 +196,9 @@ def run_ours(args):
 
     r = R.Renderer([local_rank])
     r.set_scene(scene)
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated (non-default) stream: the library enqueues on exactly this stream, so torch CUDA events see it
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     tile = torch.zeros((rows_pad, W, 3), dtype=torch.float32, device=dev)
     image = torch.zeros((W, H, 3), dtype=torch.float32, device=dev)  # Julia column-major H x W x RGB
     gathered = torch.zeros((G, rows_pad, W, 3), dtype=torch.float32, device=dev) if (G > 1 and rank == 0) else None

@@ -91,6 +91,7 @@ typedef struct rtw_ctx rtw_ctx;
 #define RTW_OPT_COLLECT_TIMING 4  /* 1 = record per-stage CUDA-event timings into rtw_stats (default 1) */
 #define RTW_OPT_RAYS_PER_LANE 5   /* paths traced concurrently by one lane: 1, 2 or 4 (0 = library default) */
 #define RTW_OPT_SWEEP 6           /* RTW_SWEEP_*: inner-loop variant of the sphere-list sweep          */
+#define RTW_OPT_COOP 7            /* lanes sharing sphere loads in the packed sweep: 1, 2 or 4 (0 = default) */
 
 #define RTW_SWEEP_DEFAULT 0       /* library default (the fastest measured)                           */
 #define RTW_SWEEP_BRANCH 1        /* test + immediate root selection under a branch                    */
@@ -158,7 +159,8 @@ RTW_API int rtw_render_scene(rtw_ctx* ctx, const float* geom4, const float* mat4
  *   i0 = row_start, row_start + row_stride, ...  (< H)
  * of the image on device `device_slot` (index into the ctx's device list) and writes a compact tile
  *   d_tile[(k*W + j0)*3 + c],  k = 0 .. n_rows-1   (row-major, post-gamma Float32)
- * into DEVICE memory.  `stream` is a cudaStream_t (NULL = the context's own stream); the call only
+ * into DEVICE memory.  `stream` is a cudaStream_t (NULL = the context's own stream; to target the legacy
+ * default stream pass cudaStreamLegacy, i.e. (void*)1); the call only
  * enqueues work on it and returns -- synchronise the stream before reading d_tile or stats.
  * With row_start = 0, row_stride = 1 and column_major != 0 the tile is written in the Julia layout of
  * rtw_render instead.
@@ -183,7 +185,8 @@ RTW_API int rtw_assemble_tiles_device(rtw_ctx* ctx, int device_slot, const float
 /*
  * FP32 issue microbenchmark on device `device_slot`: independent FFMA chains on every SM.
  *   variant 0: pure FFMA;  variant 1: the scalar mask sweep's own mix (3 FADD, 2 FMUL, 6 FFMA + 1 SHF, 1 LDS.128 per test);
- *   variant 2: the packed FP32x2 mask sweep (the same 11 lane-ops per test, two tests per instruction)
+ *   variant 2: the packed FP32x2 mask sweep (the same 11 lane-ops per test, two tests per instruction);
+ *   variants 3, 4: variant 2 with 2 / 4 cooperating lanes per sphere load (RTW_OPT_COOP)
  * Writes achieved FP32 instructions/s (lane-instructions, i.e. warp instructions x 32) and the kernel time.
  */
 RTW_API int rtw_measure_fp32_peak(rtw_ctx* ctx, int device_slot, int variant, double* fp32_instr_per_s, float* ms);

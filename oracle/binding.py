@@ -73,7 +73,7 @@ def load() -> C.CDLL:
     lib.rtwo_skycolor_f32.argtypes = [f3, d3]
     lib.rtwo_skycolor_f64.argtypes = [d3, d3]
     lib.rtwo_philox4x32_10.argtypes = [u32p, u32p, u32p]
-    lib.rtwo_path_stream_f32.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, f3]
+    lib.rtwo_path_stream_f32.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, f3]
     lib.rtwo_xoroshiro_u64.argtypes = [C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
     lib.rtwo_xoroshiro_f32.argtypes = [C.c_uint64, C.c_int, f3]
     lib.rtwo_path_f32.argtypes = [f3, f3, u32p, C.c_uint32, C.POINTER(rtwo_camera_f32), C.c_int, C.c_int, C.c_uint64,
@@ -152,10 +152,11 @@ def philox4x32_10(ctr, key):
     return [int(x) for x in out]
 
 
-def path_stream(seed, pixel, sample, n):
+def path_stream(seed, pixel, sample, event, n):
+    """draws 0..n-1 of `event` of path (pixel, sample) in the production (addressed Philox) stream"""
     lib = load()
     out = np.zeros(n, dtype=np.float32)
-    lib.rtwo_path_stream_f32(seed, pixel, sample, n, out.ctypes.data_as(C.POINTER(C.c_float)))
+    lib.rtwo_path_stream_f32(seed, pixel, sample, event, n, out.ctypes.data_as(C.POINTER(C.c_float)))
     return out
 
 

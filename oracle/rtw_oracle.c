@@ -17,11 +17,13 @@
 
 typedef struct {
     int mode;
-    /* Philox4x32-10, path keyed */
+    /* Philox4x32-10, addressed by (pixel, sample, event, word position) */
     uint32_t key[2];
-    uint32_t ctr[4];
+    uint32_t pixel, sample, event;
+    uint32_t pos;       /* next word of the current event's word sequence: block = pos / 4, word = pos % 4 */
     uint32_t buf[4];
-    int pos;
+    uint32_t buf_block;
+    int buf_valid;
     /* xoroshiro128+ */
     uint64_t x, y;
 } rtwo_rng;
@@ -30,8 +32,6 @@ typedef struct {
 #define PHILOX_M1 0xCD9E8D57u
 #define PHILOX_W0 0x9E3779B9u
 #define PHILOX_W1 0xBB67AE85u
-/* 4th counter word of the render stream: ASCII "RTW1" */
-#define RTWO_STREAM_TAG 0x52545731u
 
 void rtwo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
@@ -50,20 +50,36 @@ void rtwo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
 }
 
 /*
- * Production stream (documented in DESIGN.md "RNG stream"):
+ * Production stream (documented in DESIGN.md "RNG stream"): every uniform is ADDRESSED, not drawn from a running
+ * sequence, so a GPU lane can produce any of them without carrying generator state:
  *   key     = (seed lo32, seed hi32)
- *   counter = (block, sample s0, pixel i0*W+j0, "RTW1"),  block = 0,1,2,...
- *   the k-th uniform of a path is word (k mod 4) of block (k div 4);  f32 = (word >> 9) * 2^-23
+ *   counter = (block, sample s0, pixel i0*W+j0, event)
+ *   event 0 = the primary ray (src/render.jl:30-37):  draws 0,1 = jitter du, dv (unused for the first sample);
+ *             disk attempt k (src/rand.jl:31-38) = draws 2+2k, 3+2k
+ *   event e >= 1 = scatter() at the e-th hit of the path (src/material.jl):
+ *             ball attempt a (src/rand.jl:15-22) = draws 4a, 4a+1, 4a+2  (x, y, z);  draw 3 = the dielectric coin
+ *   draw n of an event is word (n mod 4) of block (n div 4) for Float32 (Float64 takes two words per draw);
+ *   f32 = (word >> 9) * 2^-23.
  */
 static inline void rtwo_rng_begin_path(rtwo_rng* g, uint64_t seed, uint32_t pixel, uint32_t sample) {
     g->key[0] = (uint32_t)seed;
     g->key[1] = (uint32_t)(seed >> 32);
-    g->ctr[0] = 0;
-    g->ctr[1] = sample;
-    g->ctr[2] = pixel;
-    g->ctr[3] = RTWO_STREAM_TAG;
-    g->pos = 4;
+    g->pixel = pixel;
+    g->sample = sample;
+    g->event = 0;
+    g->pos = 0;
+    g->buf_valid = 0;
 }
+
+/* start the next event (no-op for the sequential xoroshiro stream) */
+static inline void rtwo_rng_next_event(rtwo_rng* g) {
+    g->event += 1;
+    g->pos = 0;
+    g->buf_valid = 0;
+}
+
+/* position the stream at draw `draw` of the current event (no-op for the sequential xoroshiro stream) */
+static inline void rtwo_rng_seek(rtwo_rng* g, uint32_t draw, uint32_t words_per_draw) { g->pos = draw * words_per_draw; }
 
 static inline uint64_t rotl64(uint64_t v, int k) { return (v << k) | (v >> (64 - k)); }
 
@@ -96,12 +112,14 @@ static inline void rtwo_rng_seed_xoroshiro(rtwo_rng* g, uint64_t seed) {
 
 static inline uint32_t rtwo_next_u32(rtwo_rng* g) {
     if (g->mode == RTWO_RNG_XOROSHIRO) return (uint32_t)xoroshiro_next(g); /* rand(rng, UInt64) % UInt32 */
-    if (g->pos == 4) {
-        rtwo_philox4x32_10(g->ctr, g->key, g->buf);
-        g->ctr[0] += 1;
-        g->pos = 0;
+    uint32_t blk = g->pos >> 2;
+    if (!g->buf_valid || g->buf_block != blk) {
+        uint32_t ctr[4] = {blk, g->sample, g->pixel, g->event};
+        rtwo_philox4x32_10(ctr, g->key, g->buf);
+        g->buf_block = blk;
+        g->buf_valid = 1;
     }
-    return g->buf[g->pos++];
+    return g->buf[(g->pos++) & 3u];
 }
 
 static inline uint64_t rtwo_next_u64(rtwo_rng* g) {
@@ -115,6 +133,7 @@ static inline uint64_t rtwo_next_u64(rtwo_rng* g) {
 
 #define RT float
 #define RT_IS_F32 1
+#define RT_WORDS_PER_DRAW 1u
 #define SFX(x) x##_f32
 #define FMA fmaf
 #define SQRT sqrtf
@@ -123,6 +142,7 @@ static inline uint64_t rtwo_next_u64(rtwo_rng* g) {
 #include "rtw_oracle_impl.h"
 #undef RT
 #undef RT_IS_F32
+#undef RT_WORDS_PER_DRAW
 #undef SFX
 #undef FMA
 #undef SQRT
@@ -131,6 +151,7 @@ static inline uint64_t rtwo_next_u64(rtwo_rng* g) {
 
 #define RT double
 #define RT_IS_F32 0
+#define RT_WORDS_PER_DRAW 2u
 #define SFX(x) x##_f64
 #define FMA fma
 #define SQRT sqrt
@@ -139,6 +160,7 @@ static inline uint64_t rtwo_next_u64(rtwo_rng* g) {
 #include "rtw_oracle_impl.h"
 #undef RT
 #undef RT_IS_F32
+#undef RT_WORDS_PER_DRAW
 #undef SFX
 #undef FMA
 #undef SQRT
@@ -198,11 +220,12 @@ int rtwo_hit_sphere_f32(const float c[3], float radius, const float o[3], const 
 void rtwo_skycolor_f32(const float dir[3], double out[3]) { skycolor_f32(mk_f32(dir[0], dir[1], dir[2]), out); }
 void rtwo_skycolor_f64(const double dir[3], double out[3]) { skycolor_f64(mk_f64(dir[0], dir[1], dir[2]), out); }
 
-void rtwo_path_stream_f32(uint64_t seed, uint32_t pixel, uint32_t sample, int n, float* out) {
+void rtwo_path_stream_f32(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t event, int n, float* out) {
     rtwo_rng g;
     memset(&g, 0, sizeof g);
     g.mode = RTWO_RNG_PHILOX;
     rtwo_rng_begin_path(&g, seed, pixel, sample);
+    g.event = event;
     for (int i = 0; i < n; ++i) out[i] = trand_f32(&g);
 }
 void rtwo_xoroshiro_u64(uint64_t seed, int n, uint64_t* out) {

@@ -43,7 +43,7 @@ extern "C" {
 #endif
 
 /* RNG stream selectors */
-#define RTWO_RNG_PHILOX 0     /* production stream: Philox4x32-10 keyed per path (documented in DESIGN.md) */
+#define RTWO_RNG_PHILOX 0     /* production stream: Philox4x32-10 addressed by (pixel, sample, event, draw) */
 #define RTWO_RNG_XOROSHIRO 1  /* reference-shaped stream: one sequential xoroshiro128+ per thread (UNVERIFIED vs Julia) */
 
 /* material kinds (flattened Material{T} subtypes, src/material.jl:3,25,37) */
@@ -104,8 +104,8 @@ void rtwo_skycolor_f64(const double dir[3], double out[3]);
 
 /* Philox4x32-10 (Salmon et al. 2011), one block */
 void rtwo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-/* first n uniforms in [0,1) of the production stream for path (pixel, sample) */
-void rtwo_path_stream_f32(uint64_t seed, uint32_t pixel, uint32_t sample, int n, float* out);
+/* draws 0..n-1 (uniforms in [0,1)) of event `event` of path (pixel, sample) in the production stream */
+void rtwo_path_stream_f32(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t event, int n, float* out);
 /* first n outputs of xoroshiro128+ seeded like RandomNumbers.jl Xoroshiro128Plus(seed) (UNVERIFIED) */
 void rtwo_xoroshiro_u64(uint64_t seed, int n, uint64_t* out);
 void rtwo_xoroshiro_f32(uint64_t seed, int n, float* out);

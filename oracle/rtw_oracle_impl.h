@@ -40,10 +40,12 @@ static inline RT SFX(trand)(rtwo_rng* g) {
 /* random_between(min,max) = trand(T)*(max-min) + min, src/rand.jl:24 (contracted to one fma) */
 static inline RT SFX(random_between)(rtwo_rng* g, RT lo, RT hi) { return FMA(SFX(trand)(g), hi - lo, lo); }
 
-/* random_vec3_in_sphere, src/rand.jl:15-22: rejection in [-1,1]^3, x,y,z drawn in order */
+/* random_vec3_in_sphere, src/rand.jl:15-22: rejection in [-1,1]^3, x,y,z drawn in order.
+ * Production stream: attempt a uses draws 4a..4a+2 of the current scatter event. */
 static inline SFX(v3) SFX(random_vec3_in_sphere)(rtwo_rng* g) {
-    for (;;) {
+    for (uint32_t a = 0;; ++a) {
         SFX(v3) p;
+        rtwo_rng_seek(g, 4u * a, RT_WORDS_PER_DRAW);
         p.x = SFX(random_between)(g, (RT)-1, (RT)1);
         p.y = SFX(random_between)(g, (RT)-1, (RT)1);
         p.z = SFX(random_between)(g, (RT)-1, (RT)1);
@@ -58,6 +60,7 @@ static inline SFX(v3) SFX(random_vec3_on_sphere)(rtwo_rng* g) {
 
 /* random_vec2_in_disk, src/rand.jl:31-38 (2-vector dot = fma(y,y, x*x)) */
 static inline void SFX(random_vec2_in_disk)(rtwo_rng* g, RT* px, RT* py) {
+    rtwo_rng_seek(g, 2u, RT_WORDS_PER_DRAW); /* production stream: disk attempt k = draws 2+2k, 3+2k of event 0 */
     for (;;) {
         RT x = SFX(random_between)(g, (RT)-1, (RT)1);
         RT y = SFX(random_between)(g, (RT)-1, (RT)1);
@@ -178,7 +181,8 @@ static inline SFX(v3) SFX(scatter)(SFX(world)* w, rtwo_rng* g, SFX(v3) d_in, con
         RT sin_t = SQRT(FMA(-cos_t, cos_t, (RT)1));           /* :45 */
         int cannot_refract = ratio * sin_t > (RT)1;           /* :46 */
         *att = SFX(mk)((RT)1, (RT)1, (RT)1);                  /* :42 */
-        /* :47 `||` short-circuits: no RNG draw on total internal reflection */
+        /* :47 `||` short-circuits: no RNG draw on total internal reflection (production stream: draw 3 of the event) */
+        rtwo_rng_seek(g, 3u, RT_WORDS_PER_DRAW);
         if (cannot_refract || SFX(reflectance)(cos_t, ratio) > SFX(trand)(g))
             return SFX(reflect)(d_in, rec->n);                /* :48 (not re-normalised) */
         return SFX(refract)(d_in, rec->n, ratio);             /* :50 */
@@ -203,6 +207,7 @@ static void SFX(ray_color)(SFX(world)* w, rtwo_rng* g, SFX(v3) o, SFX(v3) d, int
     SFX(hitrec) rec;
     if (SFX(hit_list)(w, o, d, (RT)1e-4, (RT)INFINITY, &rec)) { /* :19 */
         SFX(v3) att;
+        if (g->mode == RTWO_RNG_PHILOX) rtwo_rng_next_event(g);  /* scatter at the e-th hit = event e */
         SFX(v3) nd = SFX(scatter)(w, g, d, &rec, &att);         /* :29 */
         double inner[3];
         SFX(ray_color)(w, g, rec.p, nd, depth - 1, inner);      /* :31 (s.reflected is always true, structs.jl:43) */
@@ -245,6 +250,7 @@ static inline void SFX(sample_path)(SFX(world)* w, rtwo_rng* g, const SFX(cam)* 
     RT v = (RT)((double)(H - i1) / (double)H); /* :27 */
     RT du = (RT)0, dv = (RT)0;                 /* :31 */
     if (s1 != 1) {
+        rtwo_rng_seek(g, 0u, RT_WORDS_PER_DRAW); /* production stream: draws 0,1 of event 0 */
         du = SFX(trand)(g) / (RT)(float)W;     /* :34 (f32_image_width) */
         dv = SFX(trand)(g) / (RT)(float)H;     /* :35 */
     }

@@ -43,6 +43,7 @@ RTW_OPT_BLOCKS_PER_SM = 3
 RTW_OPT_COLLECT_TIMING = 4
 RTW_OPT_RAYS_PER_LANE = 5
 RTW_OPT_SWEEP = 6
+RTW_OPT_COOP = 7
 
 RTW_SWEEP_DEFAULT = 0
 RTW_SWEEP_BRANCH = 1

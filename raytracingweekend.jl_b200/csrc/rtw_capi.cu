@@ -56,6 +56,7 @@ struct rtw_ctx {
     int mode = RTW_MODE_FUSED;
     int rays_per_lane = 0;  // 0 = default
     int sweep = 0;          // 0 = default
+    int coop = 0;           // 0 = default
     int blocks_per_sm = 0;
     int collect_timing = 1;
 };
@@ -65,6 +66,7 @@ namespace {
 // defaults chosen by measurement on B200 (profiles/): see DESIGN.md "Kernel variants"
 constexpr int kDefaultRaysPerLane = 1;
 constexpr int kDefaultSweep = RTW_SWEEP_PACKED;
+constexpr int kDefaultCoop = 2;
 
 int fail(rtw_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg;
@@ -175,7 +177,8 @@ int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, in
         rtw::LaunchInfo li{};
         const int rays = ctx->rays_per_lane > 0 ? ctx->rays_per_lane : kDefaultRaysPerLane;
         const int sweep = ctx->sweep > 0 ? ctx->sweep : kDefaultSweep;
-        RTW_CUDA(ctx, rtw::launch_fused_trace(p, ds.num_sms, ctx->blocks_per_sm, rays, sweep, stream, &li));
+        const int coop = ctx->coop > 0 ? ctx->coop : kDefaultCoop;
+        RTW_CUDA(ctx, rtw::launch_fused_trace(p, ds.num_sms, ctx->blocks_per_sm, rays, sweep, coop, stream, &li));
         launches += li.launches;
     }
     if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[1], stream));
@@ -446,6 +449,11 @@ int rtw_set_option(rtw_ctx* ctx, int option, int64_t value) {
                 return fail(ctx, RTW_E_INVALID_ARG, "rays_per_lane must be 0 (default), 1, 2 or 4");
             ctx->rays_per_lane = (int)value;
             return RTW_OK;
+        case RTW_OPT_COOP:
+            if (value != 0 && value != 1 && value != 2 && value != 4)
+                return fail(ctx, RTW_E_INVALID_ARG, "coop must be 0 (default), 1, 2 or 4");
+            ctx->coop = (int)value;
+            return RTW_OK;
         case RTW_OPT_SWEEP:
             if (value < 0 || value > RTW_SWEEP_PACKED) return fail(ctx, RTW_E_INVALID_ARG, "unknown sweep variant");
             ctx->sweep = (int)value;
@@ -553,7 +561,7 @@ int rtw_measure_fp32_peak(rtw_ctx* ctx, int device_slot, int variant, double* fp
     if (!ctx || !fp32_instr_per_s) return RTW_E_INVALID_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (device_slot < 0 || device_slot >= (int)ctx->dev.size()) return fail(ctx, RTW_E_INVALID_ARG, "bad device_slot");
-    if (variant < 0 || variant > 2) return fail(ctx, RTW_E_INVALID_ARG, "variant must be 0, 1 or 2");
+    if (variant < 0 || variant > 4) return fail(ctx, RTW_E_INVALID_ARG, "variant must be 0..4");
     DeviceState& ds = ctx->dev[device_slot];
     RTW_CUDA(ctx, cudaSetDevice(ds.device));
     double instr = 0.0, best = 0.0;

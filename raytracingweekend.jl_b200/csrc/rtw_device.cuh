@@ -27,23 +27,28 @@ __device__ __forceinline__ f3 normalize3(f3 a) {
 }
 
 // ---------------------------------------------------------------------------------------------- RNG
-// Production stream: Philox4x32-10, key = (seed lo, seed hi), counter = (block, sample, pixel, "RTW1").
-// The k-th uniform of a path is word (k mod 4) of block (k div 4); f32 = (word >> 9) * 2^-23.
+// Production stream: Philox4x32-10, key = (seed lo, seed hi), counter = (block, sample, pixel, event).
+// Every uniform is ADDRESSED by (pixel, sample, event, draw) -- no generator state is carried in registers
+// and every Philox evaluation sits at a point where the lanes of a warp are converged:
+//   event 0 = primary ray: draws 0,1 = jitter du,dv; disk attempt k = draws 2+2k, 3+2k
+//   event e >= 1 = scatter at the e-th hit: ball attempt a = draws 4a..4a+2 (x,y,z); draw 3 = dielectric coin
+//   draw n = word (n mod 4) of block (n div 4);  f32 = (word >> 9) * 2^-23
 // This replaces the reference's per-thread sequential Xoroshiro128Plus (src/init.jl:2-12, src/rand.jl:2-13).
 constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
-constexpr uint32_t kStreamTag = 0x52545731u;  // "RTW1"
 
 struct PathRng {
-    uint32_t block;   // next Philox block index of this path
     uint32_t sample;  // counter word 1
-    uint32_t pixel;   // counter word 2
-    uint32_t b0, b1, b2, b3;
-    uint32_t pos;     // 0..4, 4 = buffer empty
+    uint32_t pixel;   // counter word 2 (global pixel index i0*W + j0)
 };
 
-__device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0,
+struct u32x4 {
+    uint32_t w0, w1, w2, w3;
+};
+
+__device__ __forceinline__ u32x4 philox_block(const PathRng& g, uint32_t event, uint32_t block, uint32_t k0,
                                               uint32_t k1) {
+    uint32_t c0 = block, c1 = g.sample, c2 = g.pixel, c3 = event;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
@@ -53,42 +58,24 @@ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
         k0 += kPhiloxW0; k1 += kPhiloxW1;
     }
-}
-
-__device__ __forceinline__ void rng_begin(PathRng& g, uint32_t pixel, uint32_t sample) {
-    g.block = 0; g.sample = sample; g.pixel = pixel; g.pos = 4;
-}
-
-__device__ __forceinline__ uint32_t rng_u32(PathRng& g, uint32_t k0, uint32_t k1) {
-    if (g.pos == 4) {
-        uint32_t c0 = g.block, c1 = g.sample, c2 = g.pixel, c3 = kStreamTag;
-        philox4x32_10(c0, c1, c2, c3, k0, k1);
-        g.b0 = c0; g.b1 = c1; g.b2 = c2; g.b3 = c3;
-        g.block += 1;
-        g.pos = 0;
-    }
-    uint32_t r = g.pos == 0 ? g.b0 : g.pos == 1 ? g.b1 : g.pos == 2 ? g.b2 : g.b3;
-    g.pos += 1;
-    return r;
+    return u32x4{c0, c1, c2, c3};
 }
 
 // trand(Float32), src/rand.jl:10-13
-__device__ __forceinline__ float rng_f32(PathRng& g, uint32_t k0, uint32_t k1) {
-    return (float)(rng_u32(g, k0, k1) >> 9) * 1.1920928955078125e-07f;  // 2^-23
-}
+__device__ __forceinline__ float u01(uint32_t w) { return (float)(w >> 9) * 1.1920928955078125e-07f; }  // 2^-23
 // random_between(-1, 1) = trand*(max-min)+min, src/rand.jl:24
-__device__ __forceinline__ float rng_pm1(PathRng& g, uint32_t k0, uint32_t k1) {
-    return fmaf(rng_f32(g, k0, k1), 2.0f, -1.0f);
-}
+__device__ __forceinline__ float pm1(uint32_t w) { return fmaf(u01(w), 2.0f, -1.0f); }
 
-// normalize(random_vec3_in_sphere), src/rand.jl:15-22,29
-__device__ __forceinline__ f3 rng_unit_vector(PathRng& g, uint32_t k0, uint32_t k1) {
-    f3 p;
-    do {
-        p.x = rng_pm1(g, k0, k1);
-        p.y = rng_pm1(g, k0, k1);
-        p.z = rng_pm1(g, k0, k1);
-    } while (!(dot3(p, p) <= 1.0f));
+// normalize(random_vec3_in_sphere), src/rand.jl:15-22,29: rejection in the cube; attempt 0 comes from `b0`
+// (block 0 of the event, already evaluated by the caller with the warp converged), attempt a from block a.
+__device__ __forceinline__ f3 rng_unit_vector(const PathRng& g, uint32_t event, u32x4 b0, uint32_t k0, uint32_t k1) {
+    f3 p = mk3(pm1(b0.w0), pm1(b0.w1), pm1(b0.w2));
+    uint32_t a = 1;
+    while (!(dot3(p, p) <= 1.0f)) {
+        u32x4 b = philox_block(g, event, a, k0, k1);
+        p = mk3(pm1(b.w0), pm1(b.w1), pm1(b.w2));
+        ++a;
+    }
     return normalize3(p);
 }
 
@@ -98,14 +85,30 @@ struct DevCamera {  // the fields of Camera{Float32} get_ray reads (src/camera.j
     float lens_radius;
 };
 
-// get_ray(c, s, t), src/camera.jl:43-48 (the disk sample is always drawn, :44)
-__device__ __forceinline__ void get_ray(const DevCamera& c, PathRng& g, uint32_t k0, uint32_t k1, float s, float t,
-                                        f3& o, f3& d) {
-    float px, py;
-    do {  // random_vec2_in_disk, src/rand.jl:31-38
-        px = rng_pm1(g, k0, k1);
-        py = rng_pm1(g, k0, k1);
-    } while (!(fmaf(py, py, px * px) <= 1.0f));
+// Primary ray of sample s0 of a pixel (src/render.jl:26-37 + get_ray, src/camera.jl:43-48).
+// u_base, v_base are the un-jittered T(j/W), T((H-i)/H); the disk sample is always drawn (camera.jl:44).
+__device__ __forceinline__ void primary_ray(const DevCamera& c, const PathRng& g, uint32_t k0, uint32_t k1,
+                                            uint32_t s0, float u_base, float v_base, float fw, float fh, f3& o,
+                                            f3& d) {
+    u32x4 b = philox_block(g, 0u, 0u, k0, k1);
+    float s = u_base, t = v_base;
+    if (s0 != 0u) {  // first sample is centred (src/render.jl:30-36); du = draw 0, dv = draw 1
+        s = u_base + __fdiv_rn(u01(b.w0), fw);
+        t = v_base + __fdiv_rn(u01(b.w1), fh);
+    }
+    // random_vec2_in_disk, src/rand.jl:31-38: attempt k = draws 2+2k, 3+2k
+    float px = pm1(b.w2), py = pm1(b.w3);
+    uint32_t blk = 1;
+    while (!(fmaf(py, py, px * px) <= 1.0f)) {
+        b = philox_block(g, 0u, blk, k0, k1);
+        px = pm1(b.w0);
+        py = pm1(b.w1);
+        if (!(fmaf(py, py, px * px) <= 1.0f)) {
+            px = pm1(b.w2);
+            py = pm1(b.w3);
+        }
+        ++blk;
+    }
     float rx = c.lens_radius * px, ry = c.lens_radius * py;
     f3 off = mk3(fmaf(c.v.x, ry, c.u.x * rx), fmaf(c.v.y, ry, c.u.y * rx), fmaf(c.v.z, ry, c.u.z * rx));
     o = mk3(c.origin.x + off.x, c.origin.y + off.y, c.origin.z + off.z);
@@ -167,23 +170,27 @@ __device__ __forceinline__ f3 refract3(f3 d, f3 n, float ratio) {
 // HitRecord reconstruction (src/hit.jl:31-34, 6-10) + scatter (src/material.jl) for the closest sphere.
 // In: ray (o,d), root t, sphere geometry g, material m (albedo + fuzz|ir), kind.
 // Out: o,d replaced by the scattered ray; att = attenuation.
-__device__ __forceinline__ void shade_hit(f3& o, f3& d, float t, float4 g, float4 m, uint32_t kind, PathRng& rng,
-                                          uint32_t k0, uint32_t k1, f3& att) {
+// `event` = index of this hit along the path (1, 2, ...): addresses the scatter's random draws.
+__device__ __forceinline__ void shade_hit(f3& o, f3& d, float t, float4 g, float4 m, uint32_t kind,
+                                          const PathRng& rng, uint32_t event, uint32_t k0, uint32_t k1, f3& att) {
+    const u32x4 b0 = philox_block(rng, event, 0u, k0, k1);  // evaluated by every shading lane together
     f3 p = mk3(fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z));                       // point(), hit.jl:3
     f3 on = mk3(__fdiv_rn(p.x - g.x, g.w), __fdiv_rn(p.y - g.y, g.w), __fdiv_rn(p.z - g.z, g.w));  // hit.jl:33
     bool front = dot3(d, on) < 0.0f;                                                         // hit.jl:7
     f3 n = front ? on : mk3(-on.x, -on.y, -on.z);                                            // hit.jl:8
     f3 nd;
-    if (kind == 0u) {  // Lambertian, material.jl:13-23
-        f3 rv = rng_unit_vector(rng, k0, k1);
-        f3 sd = mk3(n.x + rv.x, n.y + rv.y, n.z + rv.z);
-        // near_zero: squared length (Float32) promoted and compared with the Float64 literal 1e-5, vec.jl:20
-        nd = ((double)dot3(sd, sd) < 1e-5) ? n : normalize3(sd);
-        att = mk3(m.x, m.y, m.z);
-    } else if (kind == 1u) {  // Metal, material.jl:31-34 (unit vector drawn even when fuzz == 0; never absorbs)
-        f3 refl = reflect3(d, n);
-        f3 rv = rng_unit_vector(rng, k0, k1);
-        nd = normalize3(mk3(fmaf(m.w, rv.x, refl.x), fmaf(m.w, rv.y, refl.y), fmaf(m.w, rv.z, refl.z)));
+    if (kind != 2u) {
+        // Lambertian (material.jl:13-23) and Metal (material.jl:31-34) both draw one unit vector first (Metal even
+        // when fuzz == 0): one shared rejection loop keeps the two materials converged
+        f3 rv = rng_unit_vector(rng, event, b0, k0, k1);
+        if (kind == 0u) {
+            f3 sd = mk3(n.x + rv.x, n.y + rv.y, n.z + rv.z);
+            // near_zero: squared length (Float32) promoted and compared with the Float64 literal 1e-5, vec.jl:20
+            nd = ((double)dot3(sd, sd) < 1e-5) ? n : normalize3(sd);
+        } else {  // never absorbs (Scatter.reflected is always true, structs.jl:43)
+            f3 refl = reflect3(d, n);
+            nd = normalize3(mk3(fmaf(m.w, rv.x, refl.x), fmaf(m.w, rv.y, refl.y), fmaf(m.w, rv.z, refl.z)));
+        }
         att = mk3(m.x, m.y, m.z);
     } else {  // Dielectric, material.jl:41-53
         float ratio = front ? __fdiv_rn(1.0f, m.w) : m.w;
@@ -191,8 +198,8 @@ __device__ __forceinline__ void shade_hit(f3& o, f3& d, float t, float4 g, float
         float sin_t = __fsqrt_rn(fmaf(-cos_t, cos_t, 1.0f));
         bool cannot_refract = ratio * sin_t > 1.0f;
         att = mk3(1.0f, 1.0f, 1.0f);
-        // `||` short-circuits (material.jl:47): no draw on total internal reflection
-        if (cannot_refract || reflectance(cos_t, ratio) > rng_f32(rng, k0, k1))
+        // `||` short-circuits (material.jl:47): the coin (draw 3 of the event) is ignored on total internal reflection
+        if (cannot_refract || reflectance(cos_t, ratio) > u01(b0.w3))
             nd = reflect3(d, n);  // not re-normalised, material.jl:48
         else
             nd = refract3(d, n, ratio);

@@ -150,25 +150,35 @@ __device__ __forceinline__ float4 pair_layout_fetch(const float4* __restrict__ t
     return make_float4(f[0], f[2], f[4], f[6]);
 }
 
-template <int R, int kBlock>
+// Lane cooperation (kCoop = 1, 2 or 4): an LDS.128 delivers 512 B to the warp and the shared-memory pipe moves
+// 128 B/clk/SM, so one broadcast load per 2 tests caps the loop near 70 % of the FP32 pipe.  With kCoop > 1 the
+// kCoop lanes of an aligned group exchange their rays by shuffle; each lane then tests ALL kCoop rays of its group
+// (slots) against every kCoop-th sphere pair, so one loaded pair feeds 2*kCoop tests.  Results are merged back by
+// shuffle with the list-order tie rule (equal t => later sphere, src/hit.jl:24-26,44-46).
+// Sphere pair P of a "super-chunk" (16*kCoop pairs = 32*kCoop spheres) is tested by lane h = P mod kCoop as its
+// i-th pair, i = P div kCoop; bit (31 - 2i - half) of the lane's mask word for that super-chunk.
+template <int NS, int kCoop, int kBlock>
 __device__ __forceinline__ void sweep_tile_packed(const float4* __restrict__ tile, uint32_t count, uint32_t k_base,
-                                                  uint32_t* __restrict__ s_mask, const f3 (&o)[R], const f3 (&d)[R],
-                                                  const bool (&alive)[R], float (&best_t)[R], int (&best_k)[R]) {
+                                                  uint32_t coop_h, uint32_t* __restrict__ s_mask, const f3 (&o)[NS],
+                                                  const f3 (&d)[NS], const bool (&alive)[NS], float (&best_t)[NS],
+                                                  int (&best_k)[NS]) {
     const float tmin = 1e-4f;
-    const uint32_t nchunks = (count + 31u) >> 5;
-    uint32_t summary[R];
+    constexpr uint32_t kSuper = 32u * kCoop;  // spheres per super-chunk
+    const uint32_t nsc = (count + kSuper - 1u) / kSuper;
+    uint32_t summary[NS];
 #pragma unroll
-    for (int r = 0; r < R; ++r) summary[r] = 0u;
-    for (uint32_t c = 0; c < nchunks; ++c) {
-        const float4* ch = tile + c * 32u;  // 16 pairs x 2 float4
-        uint32_t m[R];
+    for (int r = 0; r < NS; ++r) summary[r] = 0u;
+    const float4* lane_base = tile + coop_h * 2u;  // this lane's first pair of each super-chunk
+    for (uint32_t c = 0; c < nsc; ++c) {
+        const float4* ch = lane_base + c * kSuper;  // kSuper spheres = kSuper float4 of pair layout
+        uint32_t m[NS];
 #pragma unroll
-        for (int r = 0; r < R; ++r) m[r] = 0u;
+        for (int r = 0; r < NS; ++r) m[r] = 0u;
 #pragma unroll
-        for (int p = 0; p < 16; ++p) {
-            const float4 A = ch[2 * p], B = ch[2 * p + 1];
+        for (int i = 0; i < 16; ++i) {
+            const float4 A = ch[2 * kCoop * i], B = ch[2 * kCoop * i + 1];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
+            for (int r = 0; r < NS; ++r) {
                 // oc = o - c (src/hit.jl:13) for both spheres of the pair
                 const float2 ocx = __fadd2_rn(dup2(o[r].x), neg2(A.x, A.y));
                 const float2 ocy = __fadd2_rn(dup2(o[r].y), neg2(A.z, A.w));
@@ -186,13 +196,13 @@ __device__ __forceinline__ void sweep_tile_packed(const float4* __restrict__ til
             }
         }
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            s_mask[(c * R + r) * kBlock] = m[r];
+        for (int r = 0; r < NS; ++r) {
+            s_mask[(c * NS + r) * kBlock] = m[r];
             summary[r] |= (m[r] != 0xffffffffu ? 1u : 0u) << c;
         }
     }
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
+    for (int r = 0; r < NS; ++r) {
         if (!alive[r]) continue;
         uint32_t sum = summary[r], cand = 0u, c = 0u;
         for (;;) {
@@ -200,14 +210,12 @@ __device__ __forceinline__ void sweep_tile_packed(const float4* __restrict__ til
                 if (sum == 0u) break;
                 c = (uint32_t)__ffs((int)sum) - 1u;
                 sum &= sum - 1u;
-                cand = ~s_mask[(c * R + r) * kBlock];
-                uint32_t valid = count - c * 32u;
-                if (valid < 32u) cand &= 0xffffffffu << (32u - valid);
-                if (cand == 0u) continue;
+                cand = ~s_mask[(c * NS + r) * kBlock];
             }
             uint32_t j = (uint32_t)__clz((int)cand);
             cand &= ~(0x80000000u >> j);
-            uint32_t kl = c * 32u + j;
+            uint32_t kl = c * kSuper + 2u * ((j >> 1) * kCoop + coop_h) + (j & 1u);
+            if (kl >= count) continue;  // zero padding of the last super-chunk
             float4 s = pair_layout_fetch(tile, kl);
             float hb;
             float disc = sphere_disc(s, o[r], d[r], hb);  // scalar redo: bit-identical to the packed value
@@ -216,10 +224,52 @@ __device__ __forceinline__ void sweep_tile_packed(const float4* __restrict__ til
     }
 }
 
+// One tile for the R slots of a lane, through the sweep variant SWEEP; with kCoop > 1 (packed sweep, R == 1) the
+// rays of the lane group are exchanged first and the per-lane partial results merged afterwards.
+template <int R, int SWEEP, int kCoop, int kBlock>
+__device__ __forceinline__ void sweep_tile(const float4* __restrict__ tile, uint32_t count, uint32_t k_base,
+                                           uint32_t* __restrict__ s_mask, const f3 (&o)[R], const f3 (&d)[R],
+                                           const bool (&alive)[R], float (&best_t)[R], int (&best_k)[R]) {
+    if constexpr (SWEEP == kSweepBranch) {
+        sweep_tile_branch<R>(tile, count, k_base, o, d, alive, best_t, best_k);
+    } else if constexpr (SWEEP == kSweepMask) {
+        sweep_tile_mask<R, kBlock>(tile, count, k_base, s_mask, o, d, alive, best_t, best_k);
+    } else if constexpr (kCoop == 1) {
+        sweep_tile_packed<R, 1, kBlock>(tile, count, k_base, 0u, s_mask, o, d, alive, best_t, best_k);
+    } else {
+        static_assert(R == 1 || kCoop == 1, "lane cooperation is implemented for one path per lane");
+        const uint32_t h = threadIdx.x & (kCoop - 1);
+        f3 so[kCoop], sd[kCoop];
+        bool sa[kCoop];
+        float bt[kCoop];
+        int bk[kCoop];
+#pragma unroll
+        for (int q = 0; q < kCoop; ++q) {  // slot q holds the ray of lane (lane ^ q)
+            so[q] = mk3(__shfl_xor_sync(kFullMask, o[0].x, q), __shfl_xor_sync(kFullMask, o[0].y, q),
+                        __shfl_xor_sync(kFullMask, o[0].z, q));
+            sd[q] = mk3(__shfl_xor_sync(kFullMask, d[0].x, q), __shfl_xor_sync(kFullMask, d[0].y, q),
+                        __shfl_xor_sync(kFullMask, d[0].z, q));
+            sa[q] = __shfl_xor_sync(kFullMask, alive[0] ? 1 : 0, q) != 0;
+            bt[q] = __int_as_float(0x7f800000);
+            bk[q] = -1;
+        }
+        sweep_tile_packed<kCoop, kCoop, kBlock>(tile, count, k_base, h, s_mask, so, sd, sa, bt, bk);
+#pragma unroll
+        for (int q = 0; q < kCoop; ++q) {  // lane ^ q holds, in ITS slot q, the partial result for my ray
+            const float pt = __shfl_xor_sync(kFullMask, bt[q], q);
+            const int pk = __shfl_xor_sync(kFullMask, bk[q], q);
+            if (pk >= 0 && (best_k[0] < 0 || pt < best_t[0] || (pt == best_t[0] && pk > best_k[0]))) {
+                best_t[0] = pt;
+                best_k[0] = pk;
+            }
+        }
+    }
+}
+
 // ---- the persistent fused kernel ------------------------------------------------------------------------------
 // kMulti = false: the whole list (<= kTileSpheres) is staged once; warps then run free of CTA barriers.
 // kMulti = true : the list is streamed per bounce through two 16 KB TMA buffers, CTA-synchronously.
-template <int R, int SWEEP, bool kMulti>
+template <int R, int SWEEP, bool kMulti, int kCoop>
 __global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
     fused_trace_kernel(const __grid_constant__ TraceParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -229,7 +279,8 @@ __global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
     const float4* __restrict__ g_src = SWEEP == kSweepPacked ? P.geom_pairs : P.geom;
     const uint32_t n_stage = SWEEP == kSweepPacked ? ((n + 1u) & ~1u) : n;  // spheres worth of bytes to copy
     const uint32_t n_tiles = kMulti ? (n + kTileSpheres - 1u) / kTileSpheres : 1u;
-    const uint32_t tile_cap = kMulti ? kTileSpheres : ((n + 31u) & ~31u);  // spheres per buffer (multiple of 32)
+    constexpr uint32_t kGran = 32u * kCoop;  // buffers hold whole (super-)chunks
+    const uint32_t tile_cap = kMulti ? kTileSpheres : ((n + kGran - 1u) / kGran) * kGran;
     float4* s_tile0 = reinterpret_cast<float4*>(smem_raw);
     float4* s_tile1 = s_tile0 + tile_cap;
     uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tile0 + (kMulti ? 2u : 1u) * tile_cap) + threadIdx.x;
@@ -273,7 +324,8 @@ __global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
         pix_local[r] = 0u;
         depth_left[r] = 0;
         alive[r] = false;
-        rng_begin(rng[r], 0u, 0u);
+        rng[r].sample = 0u;
+        rng[r].pixel = 0u;
     }
     bool done = false;  // lane-level: no more tickets
     uint32_t seg_count = 0;
@@ -327,12 +379,9 @@ __global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
                 // u = T(j/W), v = T((H-i)/H): quotient in Float64, rounded to Float32 (src/render.jl:26-27)
                 float su = (float)((double)(col + 1u) / (double)P.W);
                 float sv = (float)((double)((uint32_t)P.H - 1u - i0) / (double)P.H);
-                rng_begin(rng[r], i0 * (uint32_t)P.W + col, s0);
-                if (s0 != 0u) {  // first sample is centred (src/render.jl:30-36); du is drawn before dv
-                    su = su + __fdiv_rn(rng_f32(rng[r], k0, k1), (float)P.W);
-                    sv = sv + __fdiv_rn(rng_f32(rng[r], k0, k1), (float)P.H);
-                }
-                get_ray(P.cam, rng[r], k0, k1, su, sv, o[r], d[r]);
+                rng[r].pixel = i0 * (uint32_t)P.W + col;
+                rng[r].sample = s0;
+                primary_ray(P.cam, rng[r], k0, k1, s0, su, sv, (float)P.W, (float)P.H, o[r], d[r]);
                 thr_r[r] = thr_g[r] = thr_b[r] = 1.0;
                 depth_left[r] = P.max_depth;
                 pix_local[r] = pl;
@@ -357,9 +406,7 @@ __global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
             best_k[r] = -1;
         }
         if (!kMulti) {
-            if (SWEEP == kSweepPacked) sweep_tile_packed<R, kTraceBlock>(s_tile0, n, 0u, s_mask, o, d, alive, best_t, best_k);
-            else if (SWEEP == kSweepMask) sweep_tile_mask<R, kTraceBlock>(s_tile0, n, 0u, s_mask, o, d, alive, best_t, best_k);
-            else sweep_tile_branch<R>(s_tile0, n, 0u, o, d, alive, best_t, best_k);
+            sweep_tile<R, SWEEP, kCoop, kTraceBlock>(s_tile0, n, 0u, s_mask, o, d, alive, best_t, best_k);
         } else {
             if (threadIdx.x == 0) {  // prologue: tile 0 -> buffer 0
                 uint32_t cnt = n_stage < kTileSpheres ? n_stage : kTileSpheres;
@@ -379,9 +426,7 @@ __global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
                 const float4* tile = (t & 1u) ? s_tile1 : s_tile0;
                 if (t & 1u) { mbar_wait(&s_bar[1], bar_phase1); bar_phase1 ^= 1u; }
                 else { mbar_wait(&s_bar[0], bar_phase0); bar_phase0 ^= 1u; }
-                if (SWEEP == kSweepPacked) sweep_tile_packed<R, kTraceBlock>(tile, cnt, base, s_mask, o, d, alive, best_t, best_k);
-                else if (SWEEP == kSweepMask) sweep_tile_mask<R, kTraceBlock>(tile, cnt, base, s_mask, o, d, alive, best_t, best_k);
-                else sweep_tile_branch<R>(tile, cnt, base, o, d, alive, best_t, best_k);
+                sweep_tile<R, SWEEP, kCoop, kTraceBlock>(tile, cnt, base, s_mask, o, d, alive, best_t, best_k);
                 __syncthreads();  // the buffer may be overwritten by the prefetch issued in the next iteration
             }
         }
@@ -407,7 +452,7 @@ __global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
                 float4 m = __ldg(P.mat + best_k[r]);
                 uint32_t kind = __ldg(P.kind + best_k[r]);
                 f3 att;
-                shade_hit(o[r], d[r], best_t[r], g, m, kind, rng[r], k0, k1, att);
+                shade_hit(o[r], d[r], best_t[r], g, m, kind, rng[r], (uint32_t)(P.max_depth - depth_left[r]), k0, k1, att);
                 thr_r[r] = __dmul_rn(thr_r[r], (double)att.x);
                 thr_g[r] = __dmul_rn(thr_g[r], (double)att.y);
                 thr_b[r] = __dmul_rn(thr_b[r], (double)att.z);
@@ -492,10 +537,10 @@ __global__ void __launch_bounds__(kPeakBlock) fp32_peak_ffma_kernel(float* out, 
 
 // the sweep's own instruction mix (mask variant: 11 FP32 + 1 SHF per test, 1 LDS.128 per R tests) with no
 // candidate ever resolved; ray data comes from memory so nothing is constant-folded
-template <int R, bool kPacked>
+template <int R, bool kPacked, int kCoopPeak>
 __global__ void __launch_bounds__(kPeakBlock) fp32_peak_sweep_kernel(float* out, const float* __restrict__ rays) {
     __shared__ float4 s_geom[kPeakSpheres];
-    __shared__ uint32_t s_mask_peak[(kPeakSpheres / 32) * R * kPeakBlock];
+    __shared__ uint32_t s_mask_peak[(kPeakSpheres / 32) * R * kPeakBlock];  // (n/(32 kCoop)) super-chunks x kCoop slots
     for (int i = threadIdx.x; i < kPeakSpheres; i += blockDim.x)
         s_geom[i] = kPacked ? ((i & 1) ? make_float4(-3000.f, -3000.f, 0.5f, 0.5f) : make_float4(1000.f + (float)i, 1001.f + (float)i, 2000.f, 2000.f))
                             : make_float4(1000.f + (float)i, 2000.f, -3000.f, 0.5f);  // far off-axis: disc < 0 always
@@ -514,7 +559,7 @@ __global__ void __launch_bounds__(kPeakBlock) fp32_peak_sweep_kernel(float* out,
     }
     int hits = 0;
     for (int it = 0; it < kPeakSweeps; ++it) {
-        if (kPacked) sweep_tile_packed<R, kPeakBlock>(s_geom, kPeakSpheres, 0u, s_mask_peak + threadIdx.x, o, d, alive, best_t, best_k);
+        if (kPacked) sweep_tile<R, kSweepPacked, kCoopPeak, kPeakBlock>(s_geom, kPeakSpheres, 0u, s_mask_peak + threadIdx.x, o, d, alive, best_t, best_k);
         else sweep_tile_mask<R, kPeakBlock>(s_geom, kPeakSpheres, 0u, s_mask_peak + threadIdx.x, o, d, alive, best_t, best_k);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -531,12 +576,13 @@ __global__ void __launch_bounds__(kPeakBlock) fp32_peak_sweep_kernel(float* out,
 
 namespace {
 
-template <int R, int SWEEP, bool kMulti>
+template <int R, int SWEEP, bool kMulti, int kCoop>
 cudaError_t launch_trace_variant(const TraceParams& p, int num_sms, int blocks_per_sm_override, cudaStream_t stream,
                                  LaunchInfo* info) {
-    auto kern = fused_trace_kernel<R, SWEEP, kMulti>;
-    const uint32_t tile_cap = kMulti ? kTileSpheres : ((p.n_spheres + 31u) & ~31u);
-    const uint32_t chunks = tile_cap / 32u;
+    auto kern = fused_trace_kernel<R, SWEEP, kMulti, kCoop>;
+    constexpr uint32_t kGran = 32u * kCoop;
+    const uint32_t tile_cap = kMulti ? kTileSpheres : ((p.n_spheres + kGran - 1u) / kGran) * kGran;
+    const uint32_t chunks = tile_cap / 32u;  // mask words per lane and slot-set: (tile_cap / kGran) * kCoop
     int smem = (int)((kMulti ? 2u : 1u) * tile_cap * 16u);
     if (SWEEP != kSweepBranch) smem += (int)(chunks * R * kTraceBlock * 4u);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -565,10 +611,10 @@ cudaError_t launch_trace_variant(const TraceParams& p, int num_sms, int blocks_p
     return cudaGetLastError();
 }
 
-template <int R, int SWEEP>
+template <int R, int SWEEP, int kCoop = 1>
 cudaError_t launch_trace_tiles(const TraceParams& p, int num_sms, int bps, cudaStream_t stream, LaunchInfo* info) {
-    if (p.n_spheres <= kTileSpheres) return launch_trace_variant<R, SWEEP, false>(p, num_sms, bps, stream, info);
-    return launch_trace_variant<R, SWEEP, true>(p, num_sms, bps, stream, info);
+    if (p.n_spheres <= kTileSpheres) return launch_trace_variant<R, SWEEP, false, kCoop>(p, num_sms, bps, stream, info);
+    return launch_trace_variant<R, SWEEP, true, kCoop>(p, num_sms, bps, stream, info);
 }
 
 template <int SWEEP>
@@ -583,7 +629,11 @@ cudaError_t launch_trace_rays(const TraceParams& p, int num_sms, int bps, int R,
 }  // namespace
 
 cudaError_t launch_fused_trace(const TraceParams& p, int num_sms, int blocks_per_sm_override, int rays_per_lane,
-                               int sweep, cudaStream_t stream, LaunchInfo* info) {
+                               int sweep, int coop, cudaStream_t stream, LaunchInfo* info) {
+    if (sweep != kSweepBranch && sweep != kSweepMask && rays_per_lane == 1 && coop > 1) {
+        if (coop == 2) return launch_trace_tiles<1, kSweepPacked, 2>(p, num_sms, blocks_per_sm_override, stream, info);
+        return launch_trace_tiles<1, kSweepPacked, 4>(p, num_sms, blocks_per_sm_override, stream, info);
+    }
     if (sweep == kSweepBranch) return launch_trace_rays<kSweepBranch>(p, num_sms, blocks_per_sm_override, rays_per_lane, stream, info);
     if (sweep == kSweepMask) return launch_trace_rays<kSweepMask>(p, num_sms, blocks_per_sm_override, rays_per_lane, stream, info);
     return launch_trace_rays<kSweepPacked>(p, num_sms, blocks_per_sm_override, rays_per_lane, stream, info);
@@ -615,8 +665,10 @@ cudaError_t launch_fp32_peak(int variant, int num_sms, float* scratch, cudaStrea
         *fp32_instr = (double)grid * kPeakBlock * (double)kPeakIters * kPeakChains;
     } else {
         // scratch[0..5] holds a ray (origin, direction) written by the caller
-        if (variant == 1) fp32_peak_sweep_kernel<1, false><<<grid, kPeakBlock, 0, stream>>>(scratch + 64, scratch);
-        else fp32_peak_sweep_kernel<1, true><<<grid, kPeakBlock, 0, stream>>>(scratch + 64, scratch);
+        if (variant == 1) fp32_peak_sweep_kernel<1, false, 1><<<grid, kPeakBlock, 0, stream>>>(scratch + 64, scratch);
+        else if (variant == 2) fp32_peak_sweep_kernel<1, true, 1><<<grid, kPeakBlock, 0, stream>>>(scratch + 64, scratch);
+        else if (variant == 3) fp32_peak_sweep_kernel<1, true, 2><<<grid, kPeakBlock, 0, stream>>>(scratch + 64, scratch);
+        else fp32_peak_sweep_kernel<1, true, 4><<<grid, kPeakBlock, 0, stream>>>(scratch + 64, scratch);
         *fp32_instr = (double)grid * kPeakBlock * 1.0 * (double)kPeakSweeps * kPeakSpheres * 11.0;
     }
     return cudaGetLastError();

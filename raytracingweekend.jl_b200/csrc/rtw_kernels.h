@@ -41,7 +41,7 @@ constexpr int kSweepPacked = 3;  // RTW_SWEEP_PACKED
 constexpr uint32_t kTileSpheres = 1024;
 
 cudaError_t launch_fused_trace(const TraceParams& p, int num_sms, int blocks_per_sm_override, int rays_per_lane,
-                               int sweep, cudaStream_t stream, LaunchInfo* info);
+                               int sweep, int coop, cudaStream_t stream, LaunchInfo* info);
 cudaError_t launch_resolve(const unsigned long long* accum, int W, int H, int n_rows, int row_start, int row_stride,
                            int spp, double inv_scale, int column_major, float* out, cudaStream_t stream);
 cudaError_t launch_assemble(const float* tiles, int n_tiles, int W, int H, float* out, cudaStream_t stream);

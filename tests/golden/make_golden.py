@@ -40,7 +40,7 @@ def main():
     np.savez_compressed(HERE / "random_spheres_64x36_4spp_d16_seed1.npz", image=img,
                         ray_segments=np.uint64(st["ray_segments"]))
     # RNG stream vectors: first 8 uniforms of three paths
-    streams = np.stack([O.path_stream(1, p, s, 8) for p, s in [(0, 0), (12345, 7), (2073599, 999)]])
+    streams = np.stack([O.path_stream(1, p, s, e, 8) for p, s, e in [(0, 0, 0), (12345, 7, 1), (2073599, 999, 50)]])
     np.save(HERE / "philox_path_streams_seed1.npy", streams)
     print("golden fixtures written to", HERE)
 

@@ -31,5 +31,5 @@ def test_random_scene_fixtures(oracle, rtw):
 
 def test_stream_fixture(oracle):
     gold = np.load(GOLD / "philox_path_streams_seed1.npy")
-    for row, (p, s) in zip(gold, [(0, 0), (12345, 7), (2073599, 999)]):
-        assert np.array_equal(oracle.path_stream(1, p, s, 8), row)
+    for row, (p, s, e) in zip(gold, [(0, 0, 0), (12345, 7, 1), (2073599, 999, 50)]):
+        assert np.array_equal(oracle.path_stream(1, p, s, e, 8), row)

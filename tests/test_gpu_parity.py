@@ -25,13 +25,15 @@ def _compare(img_gpu, img_cpu, max_mismatch_frac=1e-3):
     return linf, n_diff
 
 
-@pytest.mark.parametrize("rays,sweep", [(1, 1), (2, 1), (1, 2), (2, 2), (4, 2), (1, 3), (2, 3), (4, 3)])
-def test_cfg1_scene_2_spheres_all_variants(rtw, oracle, renderer, scenes, rays, sweep):
+@pytest.mark.parametrize("rays,sweep,coop", [(1, 1, 1), (2, 1, 1), (1, 2, 1), (2, 2, 1), (4, 2, 1), (1, 3, 1), (2, 3, 1),
+                                             (4, 3, 1), (1, 3, 2), (1, 3, 4)])
+def test_cfg1_scene_2_spheres_all_variants(rtw, oracle, renderer, scenes, rays, sweep, coop):
     # BASELINE configs[0]: scene_2_spheres, 96x54, 16 spp, 4 bounces, Float32 (test/runtests.jl:194 shape)
     g, m, k = scenes["two"]
     cam = rtw.t_default_cam()
     renderer.set_option(rtw.RTW_OPT_RAYS_PER_LANE, rays)
     renderer.set_option(rtw.RTW_OPT_SWEEP, sweep)
+    renderer.set_option(rtw.RTW_OPT_COOP, coop)
     try:
         renderer.set_scene((g, m, k))
         img = renderer.render(cam, 96, 16, max_depth=4, seed=1)
@@ -39,11 +41,29 @@ def test_cfg1_scene_2_spheres_all_variants(rtw, oracle, renderer, scenes, rays, 
     finally:
         renderer.set_option(rtw.RTW_OPT_RAYS_PER_LANE, 0)
         renderer.set_option(rtw.RTW_OPT_SWEEP, 0)
+        renderer.set_option(rtw.RTW_OPT_COOP, 0)
     ref, _, ost = oracle.render(g, m, k, cam.as_array(), 96, 16, max_depth=4, seed=1, n_threads=1)
     _compare(img, ref)
     assert st["paths"] == ost["paths"] == 96 * 54 * 16
     assert st["ray_segments"] == ost["ray_segments"]  # identical paths, segment for segment
     assert st["sphere_tests"] == ost["sphere_tests"]
+
+
+@pytest.mark.parametrize("coop", [1, 2, 4])
+def test_random_spheres_coop_variants_identical(rtw, oracle, renderer, scenes, coop):
+    # the lane-cooperative sweep merges per-lane partial closest hits: same image bits as the oracle on the
+    # 484-sphere scene (odd super-chunk tails, ties, inside hits)
+    g, m, k = scenes["random"]
+    cam = rtw.t_cam1()
+    renderer.set_option(rtw.RTW_OPT_COOP, coop)
+    try:
+        img = renderer.render(cam, 200, 16, max_depth=16, seed=3, scene=(g, m, k))
+        st = dict(renderer.last_stats)
+    finally:
+        renderer.set_option(rtw.RTW_OPT_COOP, 0)
+    ref, _, ost = oracle.render(g, m, k, cam.as_array(), 200, 16, max_depth=16, seed=3)
+    _compare(img, ref)
+    assert st["ray_segments"] == ost["ray_segments"]
 
 
 def test_cfg2_random_spheres(rtw, oracle, renderer, scenes):
@@ -126,14 +146,16 @@ def test_large_list_streams_through_tma_tiles(rtw, oracle, renderer):
     scene = rtw.flatten_scene(rtw.scene_random_spheres(half_extent=26))  # ~2700 spheres, ragged last tile
     assert len(scene[2]) > 2 * 1024 and len(scene[2]) % 1024 != 0
     cam = rtw.t_cam1()
-    for rays, sweep in [(1, 3), (2, 3), (2, 2), (1, 1)]:
+    for rays, sweep, coop in [(1, 3, 2), (1, 3, 4), (1, 3, 1), (2, 3, 1), (2, 2, 1), (1, 1, 1)]:
         renderer.set_option(rtw.RTW_OPT_RAYS_PER_LANE, rays)
         renderer.set_option(rtw.RTW_OPT_SWEEP, sweep)
+        renderer.set_option(rtw.RTW_OPT_COOP, coop)
         try:
             img = renderer.render(cam, 128, 8, max_depth=16, scene=scene)
         finally:
             renderer.set_option(rtw.RTW_OPT_RAYS_PER_LANE, 0)
             renderer.set_option(rtw.RTW_OPT_SWEEP, 0)
+            renderer.set_option(rtw.RTW_OPT_COOP, 0)
         ref, _, ost = oracle.render(*scene, cam.as_array(), 128, 8, max_depth=16)
         _compare(img, ref)
         assert renderer.last_stats["ray_segments"] == ost["ray_segments"]

@@ -98,15 +98,41 @@ def test_philox_known_answer_vectors(oracle):
 
 
 def test_path_stream_layout(oracle):
-    # k-th uniform = word (k mod 4) of block (k div 4); counter = (block, sample, pixel, "RTW1"); f32 = (w>>9)*2^-23
+    # draw n of an event = word (n mod 4) of block (n div 4); counter = (block, sample, pixel, event); f32 = (w>>9)*2^-23
     seed, pixel, sample = 0x1234567800000001, 4321, 17
-    got = oracle.path_stream(seed, pixel, sample, 12)
     key = [seed & 0xFFFFFFFF, seed >> 32]
-    exp = []
-    for blk in range(3):
-        exp += [np.float32(w >> 9) * np.float32(2.0 ** -23) for w in oracle.philox4x32_10([blk, sample, pixel, 0x52545731], key)]
-    assert got.tolist() == [float(x) for x in exp]
-    assert got.min() >= 0.0 and got.max() < 1.0
+    for event in (0, 1, 7):
+        got = oracle.path_stream(seed, pixel, sample, event, 12)
+        exp = []
+        for blk in range(3):
+            exp += [np.float32(w >> 9) * np.float32(2.0 ** -23) for w in oracle.philox4x32_10([blk, sample, pixel, event], key)]
+        assert got.tolist() == [float(x) for x in exp]
+        assert got.min() >= 0.0 and got.max() < 1.0
+
+
+def test_addressed_draws_drive_the_path(oracle, rtw):
+    # the documented addresses: event 0 draws 0,1 = jitter, disk attempt k = draws 2+2k,3+2k;
+    # event e draws 4a..4a+2 = ball attempt a.  Re-derive one primary ray by hand from the stream.
+    cam = rtw.t_cam1()
+    W, H, i0, j0, s0, seed = 64, 36, 5, 9, 3, 1
+    st = oracle.path_stream(seed, i0 * W + j0, s0, 0, 16)
+    u = np.float32((j0 + 1) / W) + st[0] / np.float32(W)
+    v = np.float32((H - 1 - i0) / H) + st[1] / np.float32(H)
+    k = 0
+    while True:
+        px, py = np.float32(st[2 + 2 * k] * 2 - 1), np.float32(st[3 + 2 * k] * 2 - 1)
+        if px * px + py * py <= 1:
+            break
+        k += 1
+    rd = cam.lens_radius * np.array([px, py], np.float32)
+    off = cam.u * rd[0] + cam.v * rd[1]
+    d = (cam.lower_left_corner + u * cam.horizontal + v * cam.vertical - cam.origin - off).astype(np.float64)
+    d /= np.linalg.norm(d)
+    # empty scene: the path's colour is the sky colour of exactly this direction
+    empty = (np.zeros((0, 4), np.float32), np.zeros((0, 4), np.float32), np.zeros(0, np.uint32))
+    rgb, nseg = oracle.path(*empty, cam.as_array(), W, i0, j0, s0, seed=seed)
+    t = 0.5 * (d[1] + 1.0)
+    assert nseg == 1 and np.allclose(rgb, (1 - t) * np.ones(3) + t * np.array([0.5, 0.7, 1.0]), atol=1e-5)
 
 
 def test_xoroshiro_matches_host_mirror(oracle, rtw):

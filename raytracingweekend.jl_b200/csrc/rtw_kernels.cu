@@ -376,9 +376,11 @@ __global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
                 uint32_t row_local = pl / (uint32_t)P.W;
                 uint32_t col = pl - row_local * (uint32_t)P.W;
                 uint32_t i0 = (uint32_t)P.row_start + row_local * (uint32_t)P.row_stride;
-                // u = T(j/W), v = T((H-i)/H): quotient in Float64, rounded to Float32 (src/render.jl:26-27)
-                float su = (float)((double)(col + 1u) / (double)P.W);
-                float sv = (float)((double)((uint32_t)P.H - 1u - i0) / (double)P.H);
+                // u = T(j/W), v = T((H-i)/H): quotient in Float64, rounded to Float32 (src/render.jl:26-27).
+                // Both operands are integers < 2^24, so the correctly rounded Float32 quotient is the same value:
+                // rounding through Float64 (53 >= 2*24+2 bits) is innocuous for division.
+                float su = __fdiv_rn((float)(col + 1u), (float)P.W);
+                float sv = __fdiv_rn((float)((uint32_t)P.H - 1u - i0), (float)P.H);
                 rng[r].pixel = i0 * (uint32_t)P.W + col;
                 rng[r].sample = s0;
                 primary_ray(P.cam, rng[r], k0, k1, s0, su, sv, (float)P.W, (float)P.H, o[r], d[r]);

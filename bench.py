@@ -345,10 +345,16 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    # keep stdout clean for the ONE JSON line: libraries (e.g. NCCL's version banner) print to fd 1, so everything
+    # else is routed to stderr and the line is written to the real stdout
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

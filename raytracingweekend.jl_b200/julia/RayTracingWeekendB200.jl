@@ -1,0 +1,128 @@
+# RayTracingWeekendB200.jl -- the thin `ccall` shim a RayTracingWeekend.jl user loads to run the package's hot path
+# (render -> ray_color -> hit/scatter) on B200 GPUs through librtw_b200.so (C-ABI: include/rtw_b200.h).
+#
+# Everything host-side stays the reference's own Julia code: Camera/default_camera (src/camera.jl), Sphere, the
+# materials, HittableList (src/structs.jl, src/material.jl) and the scene builders (src/scenes.jl).  This module
+# adds one method, `render_b200`, with the positional signature of the reference's
+#     render(scene::HittableList, cam::Camera{T}, image_width=400, n_samples=1)          src/render.jl:8-9
+# and can `import RayTracingWeekend: render` + overload it for Camera{Float32} to be a true drop-in (see the end).
+#
+# NOTE: Julia is not installed in the build image, so this file is exercised only where `julia` exists; the
+# Python package next to it (api.py) makes the identical sequence of C-ABI calls and is what the tests drive.
+module RayTracingWeekendB200
+
+using RayTracingWeekend
+using RayTracingWeekend: Camera, HittableList, Sphere, Lambertian, Metal, Dielectric
+using Images: RGB
+
+const librtw = get(ENV, "RTW_B200_LIB", joinpath(@__DIR__, "..", "csrc", "librtw_b200.so"))
+
+const RTW_LAMBERTIAN = UInt32(0)
+const RTW_METAL      = UInt32(1)
+const RTW_DIELECTRIC = UInt32(2)
+
+"mirror of `rtw_stats` (include/rtw_b200.h)"
+struct RtwStats
+    paths::UInt64
+    ray_segments::UInt64
+    sphere_tests::UInt64
+    n_spheres::UInt32
+    image_width::Int32
+    image_height::Int32
+    rows_rendered::Int32
+    kernel_launches::Int32
+    ms_total::Float32
+    ms_trace::Float32
+    ms_resolve::Float32
+    ms_h2d::Float32
+    ms_d2h::Float32
+end
+
+mutable struct Context
+    ptr::Ptr{Cvoid}
+end
+
+function check(ctx::Ptr{Cvoid}, status::Cint)
+    status == 0 && return
+    msg = ctx == C_NULL ? "status $status" :
+          unsafe_string(ccall((:rtw_last_error, librtw), Cstring, (Ptr{Cvoid},), ctx))
+    error("rtw_b200 error $status: $msg")   # no CPU fallback on the hot path
+end
+
+"""
+    Context(devices = [0])
+
+Owns streams and device buffers on the given CUDA devices (rtw_create); rows are split over all of them.
+"""
+function Context(devices::Vector{<:Integer} = [0])
+    ids = Cint.(devices)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(C_NULL, ccall((:rtw_create, librtw), Cint, (Ptr{Cint}, Cint, Ptr{Ptr{Cvoid}}), ids, length(ids), out))
+    ctx = Context(out[])
+    finalizer(c -> (c.ptr != C_NULL && ccall((:rtw_destroy, librtw), Cint, (Ptr{Cvoid},), c.ptr); c.ptr = C_NULL), ctx)
+    ctx
+end
+
+const DEFAULT_CTX = Ref{Union{Nothing,Context}}(nothing)
+default_context() = (DEFAULT_CTX[] === nothing && (DEFAULT_CTX[] = Context()); DEFAULT_CTX[])
+
+# ---- the one piece of glue: Sphere.mat is an abstract field (src/structs.jl:34), so a HittableList is not isbits
+#      and has to be flattened into the SoA arrays of rtw_set_scene.  List order is kept (tie-break, src/hit.jl:44-46).
+matrow(m::Lambertian{Float32}) = (RTW_LAMBERTIAN, (m.albedo[1], m.albedo[2], m.albedo[3], 0f0))
+matrow(m::Metal{Float32})      = (RTW_METAL,      (m.albedo[1], m.albedo[2], m.albedo[3], m.fuzz))
+matrow(m::Dielectric{Float32}) = (RTW_DIELECTRIC, (1f0, 1f0, 1f0, m.ir))
+matrow(m) = error("rtw_b200: unsupported material $(typeof(m)) (Float32 Lambertian/Metal/Dielectric only)")
+
+function flatten(scene::HittableList)
+    n = length(scene)
+    geom = Matrix{Float32}(undef, 4, n)   # column k = {cx, cy, cz, radius}
+    mat  = Matrix{Float32}(undef, 4, n)   # column k = {albedo r,g,b, fuzz|ir|0}
+    kind = Vector{UInt32}(undef, n)
+    for (k, s) in enumerate(scene)
+        s isa Sphere{Float32} || error("rtw_b200: only Sphere{Float32} hittables are supported, got $(typeof(s))")
+        geom[1, k], geom[2, k], geom[3, k] = s.center
+        geom[4, k] = s.radius             # sign kept: a negative radius is a hollow glass shell (src/scenes.jl:35-36)
+        kind[k], row = matrow(s.mat)
+        mat[:, k] .= row
+    end
+    geom, mat, kind
+end
+
+"""
+    render_b200(scene, cam::Camera{Float32}, image_width=400, n_samples=1; max_depth=16, seed=1, ctx, stats)
+
+Drop-in for `render(scene, cam, image_width, n_samples)` (src/render.jl:8-44).  Returns `Matrix{RGB{Float32}}` of
+size (image_width ÷ 16//9, image_width), gamma-2 encoded and unclamped exactly like the reference.
+`max_depth` is `ray_color`'s `depth` (hard default 16 in the reference, src/ray_color.jl:14); `seed` plays the role
+of `reseed!()` (src/render.jl:21): the same seed gives the same image on every call, for any number of GPUs.
+"""
+function render_b200(scene::HittableList, cam::Camera{Float32}, image_width::Integer = 400, n_samples::Integer = 1;
+                     max_depth::Integer = 16, seed::Integer = 1, ctx::Context = default_context(),
+                     stats::Union{Nothing,Ref{RtwStats}} = nothing)
+    geom, mat, kind = flatten(scene)
+    H = Int(ccall((:rtw_image_height, librtw), Cint, (Cint,), image_width))
+    img = Matrix{RGB{Float32}}(undef, H, image_width)      # column-major H x W of 3 x Float32: the ABI's out_rgb layout
+    st = stats === nothing ? Ref{RtwStats}() : stats
+    camref = Ref(cam)                                      # Camera{Float32} is isbits: 22 x Float32 = rtw_camera
+    GC.@preserve geom mat kind img camref begin
+        status = ccall((:rtw_render_scene, librtw), Cint,
+                       (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt32}, UInt32, Ptr{Cvoid}, Cint, Cint, Cint, UInt64,
+                        Ptr{Float32}, Ptr{RtwStats}),
+                       ctx.ptr, geom, mat, kind, length(kind), camref, image_width, n_samples, max_depth, seed,
+                       pointer(reinterpret(Float32, vec(img))), st)
+        check(ctx.ptr, status)
+    end
+    img
+end
+
+render_b200(scene::HittableList, cam::Camera, args...; kw...) =
+    error("rtw_b200: only Camera{Float32} is supported on the CUDA path (there is no CPU fallback)")
+
+# To make it a true drop-in, overload the reference's method for Float32 cameras:
+#     import RayTracingWeekend: render
+#     render(scene::HittableList, cam::Camera{Float32}, image_width=400, n_samples=1) =
+#         RayTracingWeekendB200.render_b200(scene, cam, image_width, n_samples)
+
+export render_b200, Context, RtwStats
+
+end # module

@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--depth", type=int, default=50)
     ap.add_argument("--cpu-spp", type=int, default=0, help="spp of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--half-extent", type=int, default=11,
+                    help="grid half extent of scene_random_spheres: 11 = the reference scene (484 spheres), "
+                         "158 = BASELINE configs[4] (~100k spheres, TMA-streamed sweep)")
     return ap.parse_args()
 
 
@@ -58,11 +61,11 @@ def workload_name(args):
             f"{args.spp} spp, max_depth {args.depth}, Float32, seed 1")
 
 
-def build_scene():
+def build_scene(half_extent: int = 11):
     import rtw_b200 as R
 
     R.reseed()
-    scene = R.flatten_scene(R.scene_random_spheres())
+    scene = R.flatten_scene(R.scene_random_spheres(half_extent=half_extent))
     return R, scene, R.t_cam1()
 
 
@@ -136,7 +139,9 @@ def auto_cpu_spp(args) -> int:
     cores = os.cpu_count() or 8
     pixels = args.width * ((args.width * 9) // 16)
     target_s = 15.0
-    rays = target_s * 0.19e6 * cores  # ~0.19 Mrays/s per core
+    rays = target_s * 0.19e6 * cores  # ~0.19 Mrays/s per core on the 484-sphere scene; cost is linear in n_spheres
+    if args.half_extent != 11:
+        rays *= 484.0 / (4.0 * args.half_extent * args.half_extent)
     return max(1, min(args.spp, int(rays / (pixels * 4.1))))
 
 
@@ -147,7 +152,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    R, scene, cam = build_scene()
+    R, scene, cam = build_scene(args.half_extent)
     spp = auto_cpu_spp(args)
     spp = max(1, spp // max(1, args.steps + args.warmup)) if args.cpu_spp == 0 else spp
     for _ in range(min(args.warmup, 1)):
@@ -187,7 +192,7 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
-    R, scene, cam = build_scene()
+    R, scene, cam = build_scene(args.half_extent)
     n_spheres = len(scene[2])
     W, spp, depth = args.width, args.spp, args.depth
     H = R.image_height(W)

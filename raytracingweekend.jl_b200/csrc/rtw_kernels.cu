@@ -553,8 +553,10 @@ __global__ void __launch_bounds__(kPeakBlock) fp32_peak_sweep_kernel(float* out,
     int best_k[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        o[r] = mk3(rays[0] + (float)threadIdx.x * 1e-3f, rays[1] + (float)r, rays[2]);
-        d[r] = mk3(rays[3], rays[4], rays[5]);
+        // every component differs per lane, so nothing is uniform or shared between cooperating slots
+        const float t = (float)threadIdx.x;
+        o[r] = mk3(rays[0] + t * 1e-3f, rays[1] + (float)r + t * 2e-3f, rays[2] - t * 1e-3f);
+        d[r] = mk3(rays[3] + t * 1e-4f, rays[4] - t * 1e-4f, rays[5] + t * 2e-4f);
         alive[r] = true;
         best_t[r] = __int_as_float(0x7f800000);
         best_k[r] = -1;
@@ -570,6 +572,53 @@ __global__ void __launch_bounds__(kPeakBlock) fp32_peak_sweep_kernel(float* out,
         }
     }
     if (hits) out[blockIdx.x * blockDim.x + threadIdx.x] = (float)hits;
+}
+
+// Warp-specialisation experiment: warps [0, kSweepWarps) run the packed sweep, the remaining warps run a
+// shade-like integer/SFU mix (Philox blocks, IEEE sqrt/rcp, lane-divergent retries) until the sweep warps are done.
+// Reports only the sweep warps' FP32 work: does divergent integer work in other warps slow the sweep down?
+constexpr int kMixSweepWarps = 8;
+template <int kCoopPeak, int kOtherWarps>
+__global__ void __launch_bounds__((kMixSweepWarps + kOtherWarps) * 32)
+    fp32_peak_mixed_kernel(float* out, const float* __restrict__ rays) {
+    constexpr int kSweepThreads = kMixSweepWarps * 32;
+    __shared__ float4 s_geom[kPeakSpheres];
+    __shared__ uint32_t s_mask_peak[(kPeakSpheres / 32) * kSweepThreads];
+    __shared__ volatile int s_done;
+    for (int i = threadIdx.x; i < kPeakSpheres; i += blockDim.x)
+        s_geom[i] = (i & 1) ? make_float4(-3000.f, -3000.f, 0.5f, 0.5f) : make_float4(1000.f + (float)i, 1001.f + (float)i, 2000.f, 2000.f);
+    if (threadIdx.x == 0) s_done = 0;
+    __syncthreads();
+    const float t = (float)threadIdx.x;
+    if (threadIdx.x < kSweepThreads) {
+        f3 o[1], d[1];
+        bool alive[1] = {true};
+        float best_t[1] = {__int_as_float(0x7f800000)};
+        int best_k[1] = {-1};
+        o[0] = mk3(rays[0] + t * 1e-3f, rays[1] + t * 2e-3f, rays[2] - t * 1e-3f);
+        d[0] = mk3(rays[3] + t * 1e-4f, rays[4] - t * 1e-4f, rays[5] + t * 2e-4f);
+        int hits = 0;
+        for (int it = 0; it < kPeakSweeps; ++it) {
+            sweep_tile<1, kSweepPacked, kCoopPeak, kSweepThreads>(s_geom, kPeakSpheres, 0u, s_mask_peak + threadIdx.x, o, d, alive, best_t, best_k);
+            hits += best_k[0] >= 0;
+            o[0].x += 1e-3f;
+        }
+        if (hits) out[blockIdx.x * blockDim.x + threadIdx.x] = (float)hits;
+        if (threadIdx.x == 0) s_done = 1;  // warp 0 finishes with the others (identical work)
+    } else {
+        PathRng g{threadIdx.x, blockIdx.x};
+        uint32_t ev = 1, acc = 0;
+        float facc = 0.f;
+        while (!s_done) {
+            u32x4 b0 = philox_block(g, ev, 0u, 0x1234u, 0x5678u);
+            f3 v = rng_unit_vector(g, ev, b0, 0x1234u, 0x5678u);  // divergent rejection retries
+            f3 n = normalize3(mk3(v.x + 0.5f, v.y - 0.25f, v.z + 0.125f));
+            facc += __fdiv_rn(n.x, 0.2f) + n.y * n.z;
+            acc ^= b0.w3;
+            ++ev;
+        }
+        if (acc == 0x12345u && facc == 1.5f) out[blockIdx.x * blockDim.x + threadIdx.x] = facc;
+    }
 }
 
 }  // namespace
@@ -661,19 +710,49 @@ cudaError_t launch_assemble(const float* tiles, int n_tiles, int W, int H, float
 }
 
 cudaError_t launch_fp32_peak(int variant, int num_sms, float* scratch, cudaStream_t stream, double* fp32_instr) {
+    // variant = base + 10 * L: L > 0 limits residency to L CTAs per SM (by padding dynamic shared memory), to
+    // measure the sweep at the occupancy of the real kernel
+    const int limit = variant / 10;
+    variant %= 10;
     const int grid = num_sms * 8;
-    if (variant == 0) {
-        fp32_peak_ffma_kernel<<<grid, kPeakBlock, 0, stream>>>(scratch, 0.999f, 1e-4f);
-        *fp32_instr = (double)grid * kPeakBlock * (double)kPeakIters * kPeakChains;
-    } else {
-        // scratch[0..5] holds a ray (origin, direction) written by the caller
-        if (variant == 1) fp32_peak_sweep_kernel<1, false, 1><<<grid, kPeakBlock, 0, stream>>>(scratch + 64, scratch);
-        else if (variant == 2) fp32_peak_sweep_kernel<1, true, 1><<<grid, kPeakBlock, 0, stream>>>(scratch + 64, scratch);
-        else if (variant == 3) fp32_peak_sweep_kernel<1, true, 2><<<grid, kPeakBlock, 0, stream>>>(scratch + 64, scratch);
-        else fp32_peak_sweep_kernel<1, true, 4><<<grid, kPeakBlock, 0, stream>>>(scratch + 64, scratch);
-        *fp32_instr = (double)grid * kPeakBlock * 1.0 * (double)kPeakSweeps * kPeakSpheres * 11.0;
+    size_t dyn = 0;
+    if (limit > 0) dyn = (size_t)(227 * 1024) / (size_t)limit - 42 * 1024;  // static smem of the sweep kernels: ~40 KB
+    auto launch = [&](auto kern) -> cudaError_t {
+        if (dyn > 0) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, kPeakBlock, dyn, stream>>>(scratch + 64, scratch);
+        return cudaGetLastError();
+    };
+    *fp32_instr = (double)grid * kPeakBlock * 1.0 * (double)kPeakSweeps * kPeakSpheres * 11.0;
+    switch (variant) {
+        case 0:
+            fp32_peak_ffma_kernel<<<grid, kPeakBlock, 0, stream>>>(scratch, 0.999f, 1e-4f);
+            *fp32_instr = (double)grid * kPeakBlock * (double)kPeakIters * kPeakChains;
+            return cudaGetLastError();
+        case 1: return launch(fp32_peak_sweep_kernel<1, false, 1>);
+        case 2: return launch(fp32_peak_sweep_kernel<1, true, 1>);
+        case 3: return launch(fp32_peak_sweep_kernel<1, true, 2>);
+        case 4: return launch(fp32_peak_sweep_kernel<1, true, 4>);
+        default: break;
     }
-    return cudaGetLastError();
+    // variants 5..8: warp-specialisation experiment (8 sweep warps + 0 / 4 / 8 "shade-like" warps per CTA)
+    *fp32_instr = (double)grid * (kMixSweepWarps * 32) * (double)kPeakSweeps * kPeakSpheres * 11.0;
+    auto launch_mixed = [&](auto kern, int threads) -> cudaError_t {
+        if (dyn > 0) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, threads, dyn, stream>>>(scratch + 64, scratch);
+        return cudaGetLastError();
+    };
+    switch (variant) {
+        case 5: return launch_mixed(fp32_peak_mixed_kernel<2, 0>, kMixSweepWarps * 32);
+        case 6: return launch_mixed(fp32_peak_mixed_kernel<2, 4>, (kMixSweepWarps + 4) * 32);
+        case 7: return launch_mixed(fp32_peak_mixed_kernel<2, 8>, (kMixSweepWarps + 8) * 32);
+        default: return launch_mixed(fp32_peak_mixed_kernel<4, 8>, (kMixSweepWarps + 8) * 32);
+    }
 }
 
 }  // namespace rtw

@@ -237,3 +237,17 @@ def test_in_process_multi_device_matches_single_device(rtw, scenes):
         b = np.array(rn.render(cam, 320, 8, max_depth=16, scene=scenes["random"]))
         segn = rn.last_stats["ray_segments"]
     assert np.array_equal(a, b) and seg1 == segn
+
+
+def test_cfg5_100k_spheres_small_image(rtw, oracle, renderer):
+    # BASELINE configs[4]: the ~100k-sphere synthetic list (scenes.jl:56-76 loop generalised to -158:157).
+    # 98 TMA tiles per bounce, ragged last tile; tiny image so the oracle finishes in seconds.
+    rtw.reseed()
+    scene = rtw.flatten_scene(rtw.scene_random_spheres(half_extent=158))
+    assert 99000 < len(scene[2]) < 100000
+    cam = rtw.t_cam1()
+    img = renderer.render(cam, 48, 2, max_depth=8, scene=scene)
+    ref, _, ost = oracle.render(*scene, cam.as_array(), 48, 2, max_depth=8)
+    _compare(img, ref)
+    assert renderer.last_stats["ray_segments"] == ost["ray_segments"]
+    assert renderer.last_stats["sphere_tests"] == ost["sphere_tests"]

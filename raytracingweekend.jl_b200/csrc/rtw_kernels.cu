@@ -157,13 +157,38 @@ __device__ __forceinline__ float4 pair_layout_fetch(const float4* __restrict__ t
 // shuffle with the list-order tie rule (equal t => later sphere, src/hit.jl:24-26,44-46).
 // Sphere pair P of a "super-chunk" (16*kCoop pairs = 32*kCoop spheres) is tested by lane h = P mod kCoop as its
 // i-th pair, i = P div kCoop; bit (31 - 2i - half) of the lane's mask word for that super-chunk.
+// one sphere pair against the NS slots of a lane: 11 packed FP32 instructions + 2 funnel shifts per slot
+template <int NS>
+__device__ __forceinline__ void test_pair_packed(const float4 A, const float4 B, const f3 (&o)[NS], const f3 (&d)[NS],
+                                                 uint32_t (&m)[NS]) {
+#pragma unroll
+    for (int r = 0; r < NS; ++r) {
+        // oc = o - c (src/hit.jl:13) for both spheres of the pair
+        const float2 ocx = __fadd2_rn(dup2(o[r].x), neg2(A.x, A.y));
+        const float2 ocy = __fadd2_rn(dup2(o[r].y), neg2(A.z, A.w));
+        const float2 ocz = __fadd2_rn(dup2(o[r].z), neg2(B.x, B.y));
+        // half_b = oc . d (src/hit.jl:16), dot = fma(z,z, fma(y,y, x*x))
+        const float2 hb = __ffma2_rn(ocz, dup2(d[r].z), __ffma2_rn(ocy, dup2(d[r].y), __fmul2_rn(ocx, dup2(d[r].x))));
+        // c = oc . oc - radius^2 (src/hit.jl:17)
+        const float2 q = __ffma2_rn(ocz, ocz, __ffma2_rn(ocy, ocy, __fmul2_rn(ocx, ocx)));
+        const float2 rr = make_float2(B.z, B.w);
+        const float2 cq = __ffma2_rn(neg2(rr.x, rr.y), rr, q);
+        // discriminant = half_b^2 - c (src/hit.jl:18)
+        const float2 disc = __ffma2_rn(hb, hb, neg2(cq.x, cq.y));
+        m[r] = __funnelshift_l(__float_as_uint(disc.x), m[r], 1);  // pair i of the chunk ends at bits 31-2i, 30-2i
+        m[r] = __funnelshift_l(__float_as_uint(disc.y), m[r], 1);
+    }
+}
+
 template <int NS, int kCoop, int kBlock>
-__device__ __forceinline__ void sweep_tile_packed(const float4* __restrict__ tile, uint32_t count, uint32_t k_base,
-                                                  uint32_t coop_h, uint32_t* __restrict__ s_mask, const f3 (&o)[NS],
-                                                  const f3 (&d)[NS], const bool (&alive)[NS], float (&best_t)[NS],
-                                                  int (&best_k)[NS]) {
+__device__ __forceinline__ void sweep_tile_packed(const float4* __restrict__ tile, const float4* __restrict__ aos,
+                                                  uint32_t count, uint32_t k_base, uint32_t coop_h,
+                                                  uint32_t* __restrict__ s_mask, const f3 (&o)[NS], const f3 (&d)[NS],
+                                                  const bool (&alive)[NS], float (&best_t)[NS], int (&best_k)[NS]) {
     const float tmin = 1e-4f;
-    constexpr uint32_t kSuper = 32u * kCoop;  // spheres per super-chunk
+    constexpr uint32_t kSuper = 32u * kCoop;   // spheres per super-chunk
+    constexpr uint32_t kSuperPairs = 16u * kCoop;
+    const uint32_t npairs = (count + 1u) >> 1;
     const uint32_t nsc = (count + kSuper - 1u) / kSuper;
     uint32_t summary[NS];
 #pragma unroll
@@ -174,26 +199,19 @@ __device__ __forceinline__ void sweep_tile_packed(const float4* __restrict__ til
         uint32_t m[NS];
 #pragma unroll
         for (int r = 0; r < NS; ++r) m[r] = 0u;
+        const uint32_t pairs_here = npairs - c * kSuperPairs;  // pairs left from this super-chunk on
+        if (pairs_here >= kSuperPairs) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float4 A = ch[2 * kCoop * i], B = ch[2 * kCoop * i + 1];
+            for (int i = 0; i < 16; ++i) test_pair_packed<NS>(ch[2 * kCoop * i], ch[2 * kCoop * i + 1], o, d, m);
+        } else {
+            // ragged last super-chunk: only the pairs that exist (no padded arithmetic); left-align the mask and
+            // mark the missing tests as misses
+            const uint32_t mine = pairs_here > coop_h ? (pairs_here - coop_h + kCoop - 1u) / kCoop : 0u;
+#pragma unroll 1
+            for (uint32_t i = 0; i < mine; ++i) test_pair_packed<NS>(ch[2 * kCoop * i], ch[2 * kCoop * i + 1], o, d, m);
+            const uint32_t sh = 32u - 2u * mine;  // 2..32
 #pragma unroll
-            for (int r = 0; r < NS; ++r) {
-                // oc = o - c (src/hit.jl:13) for both spheres of the pair
-                const float2 ocx = __fadd2_rn(dup2(o[r].x), neg2(A.x, A.y));
-                const float2 ocy = __fadd2_rn(dup2(o[r].y), neg2(A.z, A.w));
-                const float2 ocz = __fadd2_rn(dup2(o[r].z), neg2(B.x, B.y));
-                // half_b = oc . d (src/hit.jl:16), dot = fma(z,z, fma(y,y, x*x))
-                const float2 hb = __ffma2_rn(ocz, dup2(d[r].z), __ffma2_rn(ocy, dup2(d[r].y), __fmul2_rn(ocx, dup2(d[r].x))));
-                // c = oc . oc - radius^2 (src/hit.jl:17)
-                const float2 q = __ffma2_rn(ocz, ocz, __ffma2_rn(ocy, ocy, __fmul2_rn(ocx, ocx)));
-                const float2 rr = make_float2(B.z, B.w);
-                const float2 cq = __ffma2_rn(neg2(rr.x, rr.y), rr, q);
-                // discriminant = half_b^2 - c (src/hit.jl:18)
-                const float2 disc = __ffma2_rn(hb, hb, neg2(cq.x, cq.y));
-                m[r] = __funnelshift_l(__float_as_uint(disc.x), m[r], 1);
-                m[r] = __funnelshift_l(__float_as_uint(disc.y), m[r], 1);
-            }
+            for (int r = 0; r < NS; ++r) m[r] = sh >= 32u ? 0xffffffffu : ((m[r] << sh) | ((1u << sh) - 1u));
         }
 #pragma unroll
         for (int r = 0; r < NS; ++r) {
@@ -201,6 +219,8 @@ __device__ __forceinline__ void sweep_tile_packed(const float4* __restrict__ til
             summary[r] |= (m[r] != 0xffffffffu ? 1u : 0u) << c;
         }
     }
+    // ---- candidate resolution: each lane walks its own candidates, slot by slot, in list order so that ties still
+    // go to the later sphere (src/hit.jl:44-46)
 #pragma unroll
     for (int r = 0; r < NS; ++r) {
         if (!alive[r]) continue;
@@ -212,13 +232,19 @@ __device__ __forceinline__ void sweep_tile_packed(const float4* __restrict__ til
                 sum &= sum - 1u;
                 cand = ~s_mask[(c * NS + r) * kBlock];
             }
-            uint32_t j = (uint32_t)__clz((int)cand);
+            const uint32_t j = (uint32_t)__clz((int)cand);
             cand &= ~(0x80000000u >> j);
-            uint32_t kl = c * kSuper + 2u * ((j >> 1) * kCoop + coop_h) + (j & 1u);
-            if (kl >= count) continue;  // zero padding of the last super-chunk
-            float4 s = pair_layout_fetch(tile, kl);
-            float hb;
-            float disc = sphere_disc(s, o[r], d[r], hb);  // scalar redo: bit-identical to the packed value
+            const uint32_t kl = c * kSuper + 2u * ((j >> 1) * kCoop + coop_h) + (j & 1u);
+            if (kl >= count) continue;  // the zero pad partner of an odd last sphere
+            const float4 s = aos ? aos[kl] : pair_layout_fetch(tile, kl);
+            // scalar redo of src/hit.jl:13-18: bit-identical to the packed values
+            const f3 oc = mk3(o[r].x - s.x, o[r].y - s.y, o[r].z - s.z);
+            const float hb = dot3(oc, d[r]);
+            const float cq = fmaf(-s.w, s.w, dot3(oc, oc));
+            // Sphere entirely behind the origin (half_b > 0 and origin outside): sqrt(disc) <= half_b in IEEE
+            // arithmetic, so both roots are <= 0 < tmin and src/hit.jl:24-28 rejects them -- skip the square root.
+            if (hb > 0.0f && cq > 0.0f) continue;
+            const float disc = fmaf(hb, hb, -cq);
             if (sphere_accept(disc, hb, tmin, best_t[r])) best_k[r] = (int)(k_base + kl);
         }
     }
@@ -227,15 +253,16 @@ __device__ __forceinline__ void sweep_tile_packed(const float4* __restrict__ til
 // One tile for the R slots of a lane, through the sweep variant SWEEP; with kCoop > 1 (packed sweep, R == 1) the
 // rays of the lane group are exchanged first and the per-lane partial results merged afterwards.
 template <int R, int SWEEP, int kCoop, int kBlock>
-__device__ __forceinline__ void sweep_tile(const float4* __restrict__ tile, uint32_t count, uint32_t k_base,
-                                           uint32_t* __restrict__ s_mask, const f3 (&o)[R], const f3 (&d)[R],
-                                           const bool (&alive)[R], float (&best_t)[R], int (&best_k)[R]) {
+__device__ __forceinline__ void sweep_tile(const float4* __restrict__ tile, const float4* __restrict__ aos,
+                                           uint32_t count, uint32_t k_base, uint32_t* __restrict__ s_mask,
+                                           const f3 (&o)[R], const f3 (&d)[R], const bool (&alive)[R],
+                                           float (&best_t)[R], int (&best_k)[R]) {
     if constexpr (SWEEP == kSweepBranch) {
         sweep_tile_branch<R>(tile, count, k_base, o, d, alive, best_t, best_k);
     } else if constexpr (SWEEP == kSweepMask) {
         sweep_tile_mask<R, kBlock>(tile, count, k_base, s_mask, o, d, alive, best_t, best_k);
     } else if constexpr (kCoop == 1) {
-        sweep_tile_packed<R, 1, kBlock>(tile, count, k_base, 0u, s_mask, o, d, alive, best_t, best_k);
+        sweep_tile_packed<R, 1, kBlock>(tile, aos, count, k_base, 0u, s_mask, o, d, alive, best_t, best_k);
     } else {
         static_assert(R == 1 || kCoop == 1, "lane cooperation is implemented for one path per lane");
         const uint32_t h = threadIdx.x & (kCoop - 1);
@@ -253,7 +280,7 @@ __device__ __forceinline__ void sweep_tile(const float4* __restrict__ tile, uint
             bt[q] = __int_as_float(0x7f800000);
             bk[q] = -1;
         }
-        sweep_tile_packed<kCoop, kCoop, kBlock>(tile, count, k_base, h, s_mask, so, sd, sa, bt, bk);
+        sweep_tile_packed<kCoop, kCoop, kBlock>(tile, aos, count, k_base, h, s_mask, so, sd, sa, bt, bk);
 #pragma unroll
         for (int q = 0; q < kCoop; ++q) {  // lane ^ q holds, in ITS slot q, the partial result for my ray
             const float pt = __shfl_xor_sync(kFullMask, bt[q], q);
@@ -282,11 +309,13 @@ __global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
     constexpr uint32_t kGran = 32u * kCoop;  // buffers hold whole (super-)chunks
     const uint32_t tile_cap = kMulti ? kTileSpheres : ((n + kGran - 1u) / kGran) * kGran;
     float4* s_tile0 = reinterpret_cast<float4*>(smem_raw);
-    float4* s_tile1 = s_tile0 + tile_cap;
-    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tile0 + (kMulti ? 2u : 1u) * tile_cap) + threadIdx.x;
+    float4* s_tile1 = s_tile0 + tile_cap;  // kMulti: second streaming buffer; else (packed sweep): AoS copy of the list
+    constexpr bool kAosCopy = !kMulti && SWEEP == kSweepPacked;
+    const float4* s_aos = kAosCopy ? s_tile1 : nullptr;
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tile0 + ((kMulti || kAosCopy) ? 2u : 1u) * tile_cap) + threadIdx.x;
 
     // zero the tile buffers once (padding entries are read by the unrolled sweep and then masked off)
-    for (uint32_t i = threadIdx.x; i < (kMulti ? 2u : 1u) * tile_cap; i += kTraceBlock)
+    for (uint32_t i = threadIdx.x; i < ((kMulti || kAosCopy) ? 2u : 1u) * tile_cap; i += kTraceBlock)
         s_tile0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (threadIdx.x == 0) {
         mbar_init(&s_bar[0], 1);
@@ -299,8 +328,9 @@ __global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
     uint32_t bar_phase0 = 0u, bar_phase1 = 0u;
     if (!kMulti) {
         if (threadIdx.x == 0 && n > 0u) {
-            mbar_arrive_expect_tx(&s_bar[0], n_stage * 16u);
+            mbar_arrive_expect_tx(&s_bar[0], n_stage * 16u + (kAosCopy ? n * 16u : 0u));
             tma_bulk_g2s(s_tile0, g_src, n_stage * 16u, &s_bar[0]);
+            if (kAosCopy) tma_bulk_g2s(s_tile1, P.geom, n * 16u, &s_bar[0]);  // candidate resolution reads AoS
         }
         if (n > 0u) mbar_wait(&s_bar[0], 0u);
     }
@@ -408,7 +438,7 @@ __global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
             best_k[r] = -1;
         }
         if (!kMulti) {
-            sweep_tile<R, SWEEP, kCoop, kTraceBlock>(s_tile0, n, 0u, s_mask, o, d, alive, best_t, best_k);
+            sweep_tile<R, SWEEP, kCoop, kTraceBlock>(s_tile0, s_aos, n, 0u, s_mask, o, d, alive, best_t, best_k);
         } else {
             if (threadIdx.x == 0) {  // prologue: tile 0 -> buffer 0
                 uint32_t cnt = n_stage < kTileSpheres ? n_stage : kTileSpheres;
@@ -428,7 +458,7 @@ __global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
                 const float4* tile = (t & 1u) ? s_tile1 : s_tile0;
                 if (t & 1u) { mbar_wait(&s_bar[1], bar_phase1); bar_phase1 ^= 1u; }
                 else { mbar_wait(&s_bar[0], bar_phase0); bar_phase0 ^= 1u; }
-                sweep_tile<R, SWEEP, kCoop, kTraceBlock>(tile, cnt, base, s_mask, o, d, alive, best_t, best_k);
+                sweep_tile<R, SWEEP, kCoop, kTraceBlock>(tile, nullptr, cnt, base, s_mask, o, d, alive, best_t, best_k);
                 __syncthreads();  // the buffer may be overwritten by the prefetch issued in the next iteration
             }
         }
@@ -563,7 +593,7 @@ __global__ void __launch_bounds__(kPeakBlock) fp32_peak_sweep_kernel(float* out,
     }
     int hits = 0;
     for (int it = 0; it < kPeakSweeps; ++it) {
-        if (kPacked) sweep_tile<R, kSweepPacked, kCoopPeak, kPeakBlock>(s_geom, kPeakSpheres, 0u, s_mask_peak + threadIdx.x, o, d, alive, best_t, best_k);
+        if (kPacked) sweep_tile<R, kSweepPacked, kCoopPeak, kPeakBlock>(s_geom, nullptr, kPeakSpheres, 0u, s_mask_peak + threadIdx.x, o, d, alive, best_t, best_k);
         else sweep_tile_mask<R, kPeakBlock>(s_geom, kPeakSpheres, 0u, s_mask_peak + threadIdx.x, o, d, alive, best_t, best_k);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -599,7 +629,7 @@ __global__ void __launch_bounds__((kMixSweepWarps + kOtherWarps) * 32)
         d[0] = mk3(rays[3] + t * 1e-4f, rays[4] - t * 1e-4f, rays[5] + t * 2e-4f);
         int hits = 0;
         for (int it = 0; it < kPeakSweeps; ++it) {
-            sweep_tile<1, kSweepPacked, kCoopPeak, kSweepThreads>(s_geom, kPeakSpheres, 0u, s_mask_peak + threadIdx.x, o, d, alive, best_t, best_k);
+            sweep_tile<1, kSweepPacked, kCoopPeak, kSweepThreads>(s_geom, nullptr, kPeakSpheres, 0u, s_mask_peak + threadIdx.x, o, d, alive, best_t, best_k);
             hits += best_k[0] >= 0;
             o[0].x += 1e-3f;
         }
@@ -634,7 +664,8 @@ cudaError_t launch_trace_variant(const TraceParams& p, int num_sms, int blocks_p
     constexpr uint32_t kGran = 32u * kCoop;
     const uint32_t tile_cap = kMulti ? kTileSpheres : ((p.n_spheres + kGran - 1u) / kGran) * kGran;
     const uint32_t chunks = tile_cap / 32u;  // mask words per lane and slot-set: (tile_cap / kGran) * kCoop
-    int smem = (int)((kMulti ? 2u : 1u) * tile_cap * 16u);
+    constexpr bool kAosCopy = !kMulti && SWEEP == kSweepPacked;
+    int smem = (int)(((kMulti || kAosCopy) ? 2u : 1u) * tile_cap * 16u);
     if (SWEEP != kSweepBranch) smem += (int)(chunks * R * kTraceBlock * 4u);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;

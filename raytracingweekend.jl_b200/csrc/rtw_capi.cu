@@ -39,6 +39,8 @@ struct DeviceState {
     float* d_image = nullptr;
     size_t image_cap = 0;
     float* d_scratch = nullptr;
+    unsigned char* d_wf = nullptr;  // RTW_MODE_WAVEFRONT path pool
+    size_t wf_cap = 0;              // bytes
     // last resident render
     rtw_stats last = {};
     cudaStream_t last_stream = nullptr;
@@ -175,11 +177,39 @@ int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, in
         p.fx_scale = std::ldexp(1.0, fx_bits);
         p.counters = ds.d_counters;
         rtw::LaunchInfo li{};
+        if (ctx->mode == RTW_MODE_WAVEFRONT) {
+            if (ctx->n_spheres > rtw::kTileSpheres)
+                return fail(ctx, RTW_E_UNSUPPORTED, "RTW_MODE_WAVEFRONT supports at most 1024 spheres; use RTW_MODE_FUSED");
+            unsigned long long want = (p.n_paths + 255ull) & ~255ull;
+            uint32_t capacity = (uint32_t)(want < (1ull << 20) ? want : (1ull << 20));
+            if (capacity < 256u) capacity = 256u;
+            rc = grow(ctx, &ds.d_wf, &ds.wf_cap, rtw::wavefront_bytes(capacity));
+            if (rc) return rc;
+            rtw::WavefrontBuffers b;
+            unsigned char* q = ds.d_wf;
+            auto take = [&](size_t bytes) { unsigned char* r = q; q += (bytes + 63) & ~(size_t)63; return r; };
+            b.capacity = capacity;
+            b.ray_o = (float4*)take((size_t)capacity * 16);
+            b.ray_d = (float4*)take((size_t)capacity * 16);
+            b.thr = (double*)take((size_t)capacity * 24);
+            b.pix_local = (uint32_t*)take((size_t)capacity * 4);
+            b.sample = (uint32_t*)take((size_t)capacity * 4);
+            b.pixel = (uint32_t*)take((size_t)capacity * 4);
+            b.depth_left = (int*)take((size_t)capacity * 4);
+            b.hit_t = (float*)take((size_t)capacity * 4);
+            b.hit_k = (int*)take((size_t)capacity * 4);
+            b.alive = (uint32_t*)take((size_t)capacity * 4);
+            for (int l = 0; l < 3; ++l) b.list[l] = (uint32_t*)take((size_t)capacity * 4);
+            b.counts = (unsigned int*)take(64);
+            RTW_CUDA(ctx, rtw::launch_wavefront_trace(p, b, ds.num_sms, (unsigned int*)(ds.h_counters + 2), stream, &li));
+            launches += li.launches;
+        } else {
         const int rays = ctx->rays_per_lane > 0 ? ctx->rays_per_lane : kDefaultRaysPerLane;
         const int sweep = ctx->sweep > 0 ? ctx->sweep : kDefaultSweep;
         const int coop = ctx->coop > 0 ? ctx->coop : kDefaultCoop;
         RTW_CUDA(ctx, rtw::launch_fused_trace(p, ds.num_sms, ctx->blocks_per_sm, rays, sweep, coop, stream, &li));
         launches += li.launches;
+        }
     }
     if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[1], stream));
     RTW_CUDA(ctx, rtw::launch_resolve(ds.d_accum, W, H, n_rows, row_start, row_stride, spp, std::ldexp(1.0, -fx_bits),
@@ -392,7 +422,7 @@ int rtw_create(const int* device_ids, int n_devices, rtw_ctx** out_ctx) {
         for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&ds.ev[i]);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ds.ev_tile, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc((void**)&ds.d_counters, 2 * sizeof(unsigned long long));
-        if (e == cudaSuccess) e = cudaMallocHost((void**)&ds.h_counters, 2 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&ds.h_counters, 4 * sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaMalloc((void**)&ds.d_scratch, 4u << 20);
         if (e != cudaSuccess) {
             (void)cudaGetLastError();
@@ -421,7 +451,7 @@ int rtw_destroy(rtw_ctx* ctx) {
         if (ds.stream) cudaStreamSynchronize(ds.stream);
         cudaFree(ds.d_geom); cudaFree(ds.d_geom_pairs); cudaFree(ds.d_mat); cudaFree(ds.d_kind);
         cudaFree(ds.d_accum); cudaFree(ds.d_counters); cudaFree(ds.d_tile);
-        cudaFree(ds.d_gather); cudaFree(ds.d_image); cudaFree(ds.d_scratch);
+        cudaFree(ds.d_gather); cudaFree(ds.d_image); cudaFree(ds.d_scratch); cudaFree(ds.d_wf);
         if (ds.h_counters) cudaFreeHost(ds.h_counters);
         for (auto& e : ds.ev) if (e) cudaEventDestroy(e);
         if (ds.ev_tile) cudaEventDestroy(ds.ev_tile);
@@ -439,7 +469,7 @@ int rtw_set_option(rtw_ctx* ctx, int option, int64_t value) {
     std::lock_guard<std::mutex> lock(ctx->mu);
     switch (option) {
         case RTW_OPT_MODE:
-            if (value != RTW_MODE_FUSED) return fail(ctx, RTW_E_UNSUPPORTED, "only RTW_MODE_FUSED is implemented");
+            if (value != RTW_MODE_FUSED && value != RTW_MODE_WAVEFRONT) return fail(ctx, RTW_E_INVALID_ARG, "unknown mode");
             ctx->mode = (int)value;
             return RTW_OK;
         case RTW_OPT_STRIP:

@@ -29,6 +29,23 @@ struct TraceParams {
     unsigned long long* counters;
 };
 
+// RTW_MODE_WAVEFRONT: the path pool in HBM (structure of arrays over `capacity` slots) and its work lists
+struct WavefrontBuffers {
+    uint32_t capacity;
+    float4* ray_o;        // origin (xyz)
+    float4* ray_d;        // unit direction (xyz)
+    double* thr;          // 3 x capacity: product of attenuations so far (Float64)
+    uint32_t* pix_local;  // accumulator pixel of the path
+    uint32_t* sample;     // Philox counter word 1
+    uint32_t* pixel;      // Philox counter word 2 (global pixel index)
+    int* depth_left;
+    float* hit_t;
+    int* hit_k;           // closest sphere; -1 miss (sky), -2 depth exhausted (black), -3 slot never used
+    uint32_t* alive;
+    uint32_t* list[3];    // 0: path ended (sky / depth) -> accumulate + regenerate; 1: Lambertian/Metal; 2: Dielectric
+    unsigned int* counts; // [0..2] list lengths, [3] rays traced in the current step
+};
+
 struct LaunchInfo {
     int grid, block, smem_bytes, blocks_per_sm, launches, rays_per_lane, sweep;
 };
@@ -42,6 +59,10 @@ constexpr uint32_t kTileSpheres = 1024;
 
 cudaError_t launch_fused_trace(const TraceParams& p, int num_sms, int blocks_per_sm_override, int rays_per_lane,
                                int sweep, int coop, cudaStream_t stream, LaunchInfo* info);
+// RTW_MODE_WAVEFRONT (rtw_wavefront.cu); synchronises `stream` internally (host-driven step loop)
+size_t wavefront_bytes(uint32_t capacity);
+cudaError_t launch_wavefront_trace(const TraceParams& p, const WavefrontBuffers& b, int num_sms, unsigned int* h_traced,
+                                   cudaStream_t stream, LaunchInfo* info);
 cudaError_t launch_resolve(const unsigned long long* accum, int W, int H, int n_rows, int row_start, int row_stride,
                            int spp, double inv_scale, int column_major, float* out, cudaStream_t stream);
 cudaError_t launch_assemble(const float* tiles, int n_tiles, int W, int H, float* out, cudaStream_t stream);

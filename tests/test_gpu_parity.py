@@ -251,3 +251,30 @@ def test_cfg5_100k_spheres_small_image(rtw, oracle, renderer):
     _compare(img, ref)
     assert renderer.last_stats["ray_segments"] == ost["ray_segments"]
     assert renderer.last_stats["sphere_tests"] == ost["sphere_tests"]
+
+
+def test_wavefront_mode_matches_fused_and_oracle(rtw, oracle, scenes):
+    # RTW_MODE_WAVEFRONT: separate regenerate / intersect / scatter kernels over a path pool in HBM with per-class
+    # work lists -- same arithmetic, same addressed stream, order-independent accumulation => identical bits
+    with rtw.Renderer([0]) as r:
+        for name, cam, W, spp, depth in [("two", rtw.t_default_cam(), 96, 16, 4), ("random", rtw.t_cam1(), 200, 8, 16),
+                                         ("bubble", rtw.t_default_cam(), 128, 8, 50)]:
+            r.set_scene(scenes[name])
+            r.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_FUSED)
+            a = np.array(r.render(cam, W, spp, max_depth=depth, seed=5))
+            sa = dict(r.last_stats)
+            r.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_WAVEFRONT)
+            b = np.array(r.render(cam, W, spp, max_depth=depth, seed=5))
+            sb = dict(r.last_stats)
+            assert np.array_equal(a, b), name
+            assert sa["ray_segments"] == sb["ray_segments"] and sb["kernel_launches"] > 10
+            ref, _, ost = oracle.render(*scenes[name], cam.as_array(), W, spp, max_depth=depth, seed=5)
+            _compare(b, ref)
+            assert sb["ray_segments"] == ost["ray_segments"]
+        # the wavefront mode keeps the whole list in one shared-memory tile
+        rtw.reseed()
+        big = rtw.flatten_scene(rtw.scene_random_spheres(half_extent=20))
+        r.set_scene(big)
+        with pytest.raises(rtw.RtwError) as e:
+            r.render(rtw.t_cam1(), 64, 1)
+        assert e.value.code == rtw._lib.RTW_E_UNSUPPORTED

@@ -180,8 +180,12 @@ int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, in
         if (ctx->mode == RTW_MODE_WAVEFRONT) {
             if (ctx->n_spheres > rtw::kTileSpheres)
                 return fail(ctx, RTW_E_UNSUPPORTED, "RTW_MODE_WAVEFRONT supports at most 1024 spheres; use RTW_MODE_FUSED");
+            // pool size: a whole number of intersect-kernel waves (3 CTAs of 256 lanes per SM), at most ~1M paths
+            const unsigned long long wave = (unsigned long long)ds.num_sms * 3ull * 256ull;
             unsigned long long want = (p.n_paths + 255ull) & ~255ull;
-            uint32_t capacity = (uint32_t)(want < (1ull << 20) ? want : (1ull << 20));
+            unsigned long long cap_max = ((1ull << 20) / wave) * wave;
+            if (cap_max == 0) cap_max = wave;
+            uint32_t capacity = (uint32_t)(want < cap_max ? want : cap_max);
             if (capacity < 256u) capacity = 256u;
             rc = grow(ctx, &ds.d_wf, &ds.wf_cap, rtw::wavefront_bytes(capacity));
             if (rc) return rc;

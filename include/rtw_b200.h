@@ -100,6 +100,8 @@ typedef struct rtw_ctx rtw_ctx;
 
 #define RTW_MODE_FUSED 0          /* one persistent kernel: raygen -> {intersect, shade} loop -> accumulate */
 #define RTW_MODE_WAVEFRONT 1      /* separate raygen / intersect / shade / accumulate kernels + compaction  */
+#define RTW_MODE_CTA_WAVEFRONT 2  /* the same stages inside persistent CTAs: path pool + work lists in shared memory
+                                     (lists <= 1024 spheres; larger lists fall back to RTW_MODE_FUSED)        */
 
 /* ---- life cycle ------------------------------------------------------------------------------ */
 

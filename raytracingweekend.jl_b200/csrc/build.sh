@@ -10,5 +10,6 @@ FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=fa
 "$NVCC" "${FLAGS[@]}" -c rtw_kernels.cu -o rtw_kernels.o
 "$NVCC" "${FLAGS[@]}" -c rtw_capi.cu -o rtw_capi.o
 "$NVCC" "${FLAGS[@]}" -c rtw_wavefront.cu -o rtw_wavefront.o
-"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a rtw_kernels.o rtw_capi.o rtw_wavefront.o -o librtw_b200.so -lpthread -ldl
+"$NVCC" "${FLAGS[@]}" -c rtw_cta_wavefront.cu -o rtw_cta_wavefront.o
+"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a rtw_kernels.o rtw_capi.o rtw_wavefront.o rtw_cta_wavefront.o -o librtw_b200.so -lpthread -ldl
 echo "built $(pwd)/librtw_b200.so"

@@ -177,7 +177,10 @@ int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, in
         p.fx_scale = std::ldexp(1.0, fx_bits);
         p.counters = ds.d_counters;
         rtw::LaunchInfo li{};
-        if (ctx->mode == RTW_MODE_WAVEFRONT) {
+        if (ctx->mode == RTW_MODE_CTA_WAVEFRONT && ctx->n_spheres <= rtw::kTileSpheres) {
+            RTW_CUDA(ctx, rtw::launch_cta_wavefront_trace(p, ds.num_sms, ctx->blocks_per_sm, stream, &li));
+            launches += li.launches;
+        } else if (ctx->mode == RTW_MODE_WAVEFRONT) {
             if (ctx->n_spheres > rtw::kTileSpheres)
                 return fail(ctx, RTW_E_UNSUPPORTED, "RTW_MODE_WAVEFRONT supports at most 1024 spheres; use RTW_MODE_FUSED");
             // pool size: a whole number of intersect-kernel waves (3 CTAs of 256 lanes per SM), at most ~1M paths
@@ -473,7 +476,7 @@ int rtw_set_option(rtw_ctx* ctx, int option, int64_t value) {
     std::lock_guard<std::mutex> lock(ctx->mu);
     switch (option) {
         case RTW_OPT_MODE:
-            if (value != RTW_MODE_FUSED && value != RTW_MODE_WAVEFRONT) return fail(ctx, RTW_E_INVALID_ARG, "unknown mode");
+            if (value != RTW_MODE_FUSED && value != RTW_MODE_WAVEFRONT && value != RTW_MODE_CTA_WAVEFRONT) return fail(ctx, RTW_E_INVALID_ARG, "unknown mode");
             ctx->mode = (int)value;
             return RTW_OK;
         case RTW_OPT_STRIP:

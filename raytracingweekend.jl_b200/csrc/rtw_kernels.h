@@ -63,6 +63,9 @@ cudaError_t launch_fused_trace(const TraceParams& p, int num_sms, int blocks_per
 size_t wavefront_bytes(uint32_t capacity);
 cudaError_t launch_wavefront_trace(const TraceParams& p, const WavefrontBuffers& b, int num_sms, unsigned int* h_traced,
                                    cudaStream_t stream, LaunchInfo* info);
+// RTW_MODE_CTA_WAVEFRONT (rtw_cta_wavefront.cu): persistent CTAs, path pool and work lists in shared memory
+cudaError_t launch_cta_wavefront_trace(const TraceParams& p, int num_sms, int blocks_per_sm_override,
+                                       cudaStream_t stream, LaunchInfo* info);
 cudaError_t launch_resolve(const unsigned long long* accum, int W, int H, int n_rows, int row_start, int row_stride,
                            int spp, double inv_scale, int column_major, float* out, cudaStream_t stream);
 cudaError_t launch_assemble(const float* tiles, int n_tiles, int W, int H, float* out, cudaStream_t stream);

@@ -170,17 +170,16 @@ __device__ __forceinline__ void test_pair_packed(const float4 A, const float4 B,
     }
 }
 
+// The branch-free part of the packed sweep: fills the per-slot candidate masks of this lane in shared memory
+// (s_mask[(c*NS + r)*kBlock], super-chunk c, slot r) and returns one summary bit per non-empty mask word.
 template <int NS, int kCoop, int kBlock>
-__device__ __forceinline__ void sweep_tile_packed(const float4* __restrict__ tile, const float4* __restrict__ aos,
-                                                  uint32_t count, uint32_t k_base, uint32_t coop_h,
-                                                  uint32_t* __restrict__ s_mask, const f3 (&o)[NS], const f3 (&d)[NS],
-                                                  const bool (&alive)[NS], float (&best_t)[NS], int (&best_k)[NS]) {
-    const float tmin = 1e-4f;
+__device__ __forceinline__ void sweep_masks_packed(const float4* __restrict__ tile, uint32_t count, uint32_t coop_h,
+                                                   uint32_t* __restrict__ s_mask, const f3 (&o)[NS], const f3 (&d)[NS],
+                                                   uint32_t (&summary)[NS]) {
     constexpr uint32_t kSuper = 32u * kCoop;   // spheres per super-chunk
     constexpr uint32_t kSuperPairs = 16u * kCoop;
     const uint32_t npairs = (count + 1u) >> 1;
     const uint32_t nsc = (count + kSuper - 1u) / kSuper;
-    uint32_t summary[NS];
 #pragma unroll
     for (int r = 0; r < NS; ++r) summary[r] = 0u;
     const float4* lane_base = tile + coop_h * 2u;  // this lane's first pair of each super-chunk
@@ -209,6 +208,17 @@ __device__ __forceinline__ void sweep_tile_packed(const float4* __restrict__ til
             summary[r] |= (m[r] != 0xffffffffu ? 1u : 0u) << c;
         }
     }
+}
+
+template <int NS, int kCoop, int kBlock>
+__device__ __forceinline__ void sweep_tile_packed(const float4* __restrict__ tile, const float4* __restrict__ aos,
+                                                  uint32_t count, uint32_t k_base, uint32_t coop_h,
+                                                  uint32_t* __restrict__ s_mask, const f3 (&o)[NS], const f3 (&d)[NS],
+                                                  const bool (&alive)[NS], float (&best_t)[NS], int (&best_k)[NS]) {
+    const float tmin = 1e-4f;
+    constexpr uint32_t kSuper = 32u * kCoop;
+    uint32_t summary[NS];
+    sweep_masks_packed<NS, kCoop, kBlock>(tile, count, coop_h, s_mask, o, d, summary);
     // ---- candidate resolution: each lane walks its own candidates, slot by slot, in list order so that ties still
     // go to the later sphere (src/hit.jl:44-46)
 #pragma unroll

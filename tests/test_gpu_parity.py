@@ -263,6 +263,11 @@ def test_wavefront_mode_matches_fused_and_oracle(rtw, oracle, scenes):
             r.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_FUSED)
             a = np.array(r.render(cam, W, spp, max_depth=depth, seed=5))
             sa = dict(r.last_stats)
+            r.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_CTA_WAVEFRONT)
+            c = np.array(r.render(cam, W, spp, max_depth=depth, seed=5))
+            sc = dict(r.last_stats)
+            assert np.array_equal(a, c), name + " (CTA wavefront)"
+            assert sa["ray_segments"] == sc["ray_segments"]
             r.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_WAVEFRONT)
             b = np.array(r.render(cam, W, spp, max_depth=depth, seed=5))
             sb = dict(r.last_stats)

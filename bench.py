@@ -336,7 +336,11 @@ def run_ours(args):
                                "MEASURED_PEAKS.json holds no FP32 CUDA-core figure",
                 "sweep_mix_ceiling": fp32_sweep_mix / 1e12,
                 "achieved_tflops": tests_per_step * FLOP_PER_TEST / trace_s / 1e12 / G,
-                "traffic": None,
+                # DRAM bytes per launch of fused_trace_kernel from the committed ncu --set full capture (a 1080p slice;
+                # it is the 66 MB fixed-point accumulator, independent of spp) -- the kernel is FP32-bound, not HBM-bound
+                "traffic": measured_dram_traffic(),
+                "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu)",
+                "algorithmic_hbm_bytes": W * H * 4 * 8 if G == 1 else None,
             },
             "clocks": clocks,
         }
@@ -346,6 +350,24 @@ def run_ours(args):
     r.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def measured_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_trace_kernel_full_metrics.csv; per launch, 1920x1080 slice).  None when the file is missing."""
+    try:
+        vals = {}
+        for line in (ROOT / "profiles" / "r01_trace_kernel_full_metrics.csv").read_text().splitlines():
+            parts = line.split(",")
+            if len(parts) == 3 and parts[0].startswith("dram__bytes_"):
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(parts[1], None)
+                if scale is not None:
+                    vals[parts[0]] = float(parts[2]) * scale
+        if "dram__bytes_read.sum" in vals and "dram__bytes_write.sum" in vals:
+            return vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
+    except Exception:
+        pass
+    return None
 
 
 def main():

@@ -283,3 +283,46 @@ def test_wavefront_mode_matches_fused_and_oracle(rtw, oracle, scenes):
         with pytest.raises(rtw.RtwError) as e:
             r.render(rtw.t_cam1(), 64, 1)
         assert e.value.code == rtw._lib.RTW_E_UNSUPPORTED
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 257, 1023, 1024, 1025])
+def test_ragged_list_sizes_all_sweeps(rtw, oracle, renderer, n):
+    # the packed sweep handles odd counts (zero pad partner), ragged last super-chunks (32 / 64 / 128 spheres for
+    # 1 / 2 / 4 cooperating lanes) and the 1024-sphere tile boundary; every size must reproduce the oracle
+    rtw.reseed()
+    g, m, k = rtw.flatten_scene(rtw.scene_random_spheres(half_extent=17))  # ~1150 spheres
+    assert len(k) > 1025
+    # keep the three big spheres in play: put them first so small n still has something to hit
+    order = np.concatenate([[0], np.arange(len(k) - 3, len(k)), np.arange(1, len(k) - 3)])[:n]
+    sub = (g[order].copy(), m[order].copy(), k[order].copy())
+    cam = rtw.t_cam1()
+    ref, _, ost = oracle.render(*sub, cam.as_array(), 64, 4, max_depth=12, seed=11)
+    variants = [(1, 3, 1, 0), (1, 3, 2, 0), (1, 3, 4, 0), (2, 3, 1, 0), (1, 2, 1, 0)]
+    if n <= 1024:
+        variants += [(1, 3, 2, 1), (1, 3, 2, 2)]  # split wavefront and CTA wavefront keep the list in one tile
+    for rays, sweep, coop, mode in variants:
+        renderer.set_option(rtw.RTW_OPT_RAYS_PER_LANE, rays)
+        renderer.set_option(rtw.RTW_OPT_SWEEP, sweep)
+        renderer.set_option(rtw.RTW_OPT_COOP, coop)
+        renderer.set_option(rtw.RTW_OPT_MODE, mode)
+        try:
+            img = renderer.render(cam, 64, 4, max_depth=12, seed=11, scene=sub)
+            segs = renderer.last_stats["ray_segments"]
+        finally:
+            for opt in (rtw.RTW_OPT_RAYS_PER_LANE, rtw.RTW_OPT_SWEEP, rtw.RTW_OPT_COOP, rtw.RTW_OPT_MODE):
+                renderer.set_option(opt, 0)
+        _compare(img, ref)
+        assert segs == ost["ray_segments"], (n, rays, sweep, coop, mode)
+
+
+def test_high_seed_bits_and_many_samples(rtw, oracle, renderer, scenes):
+    # 64-bit seeds use both Philox key words; 1000 spp exercises the fixed-point accumulator scale of the headline run
+    cam = rtw.t_default_cam()
+    seed = 0xDEADBEEF12345678
+    img = renderer.render(cam, 32, 1000, max_depth=8, seed=seed, scene=scenes["four"])
+    ref, _, ost = oracle.render(*scenes["four"], cam.as_array(), 32, 1000, max_depth=8, seed=seed)
+    _compare(img, ref)
+    assert renderer.last_stats["ray_segments"] == ost["ray_segments"]
+    other = renderer.render(cam, 32, 8, max_depth=8, seed=seed ^ (1 << 40), scene=scenes["four"])
+    base = renderer.render(cam, 32, 8, max_depth=8, seed=seed, scene=scenes["four"])
+    assert not np.array_equal(np.array(other), np.array(base))  # the high key word matters

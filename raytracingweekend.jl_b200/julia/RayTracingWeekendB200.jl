@@ -107,9 +107,9 @@ function render_b200(scene::HittableList, cam::Camera{Float32}, image_width::Int
     GC.@preserve geom mat kind img camref begin
         status = ccall((:rtw_render_scene, librtw), Cint,
                        (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt32}, UInt32, Ptr{Cvoid}, Cint, Cint, Cint, UInt64,
-                        Ptr{Float32}, Ptr{RtwStats}),
+                        Ptr{Cvoid}, Ptr{RtwStats}),
                        ctx.ptr, geom, mat, kind, length(kind), camref, image_width, n_samples, max_depth, seed,
-                       pointer(reinterpret(Float32, vec(img))), st)
+                       img, st)   # img::Matrix{RGB{Float32}} is H*W*3 contiguous Float32: exactly the ABI's out_rgb
         check(ctx.ptr, status)
     end
     img

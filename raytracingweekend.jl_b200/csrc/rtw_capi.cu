@@ -136,6 +136,40 @@ int check_render_args(rtw_ctx* ctx, const rtw_camera* cam, int W, int spp, int m
     return RTW_OK;
 }
 
+// RTW_MODE_WAVEFRONT: carve the path pool (structure of arrays) out of one device allocation.  The pool holds a
+// whole number of intersect-kernel waves (3 CTAs of 256 lanes per SM), at most ~1 M paths.
+int wavefront_buffers(rtw_ctx* ctx, DeviceState& ds, unsigned long long n_paths, rtw::WavefrontBuffers* out) {
+    const unsigned long long wave = (unsigned long long)ds.num_sms * 3ull * 256ull;
+    unsigned long long cap_max = ((1ull << 20) / wave) * wave;
+    if (cap_max == 0) cap_max = wave;
+    const unsigned long long want = (n_paths + 255ull) & ~255ull;
+    uint32_t capacity = (uint32_t)(want < cap_max ? want : cap_max);
+    if (capacity < 256u) capacity = 256u;
+    int rc = grow(ctx, &ds.d_wf, &ds.wf_cap, rtw::wavefront_bytes(capacity));
+    if (rc) return rc;
+    unsigned char* q = ds.d_wf;
+    auto take = [&q](size_t bytes) {
+        unsigned char* r = q;
+        q += (bytes + 63) & ~(size_t)63;
+        return r;
+    };
+    rtw::WavefrontBuffers& b = *out;
+    b.capacity = capacity;
+    b.ray_o = (float4*)take((size_t)capacity * 16);
+    b.ray_d = (float4*)take((size_t)capacity * 16);
+    b.thr = (double*)take((size_t)capacity * 24);
+    b.pix_local = (uint32_t*)take((size_t)capacity * 4);
+    b.sample = (uint32_t*)take((size_t)capacity * 4);
+    b.pixel = (uint32_t*)take((size_t)capacity * 4);
+    b.depth_left = (int*)take((size_t)capacity * 4);
+    b.hit_t = (float*)take((size_t)capacity * 4);
+    b.hit_k = (int*)take((size_t)capacity * 4);
+    b.alive = (uint32_t*)take((size_t)capacity * 4);
+    for (int l = 0; l < 3; ++l) b.list[l] = (uint32_t*)take((size_t)capacity * 4);
+    b.counts = (unsigned int*)take(64);
+    return RTW_OK;
+}
+
 // Enqueue trace + resolve for a row subset on one device.  Output: d_out (tile row-major, or Julia column-major).
 int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, int spp, int max_depth, uint64_t seed,
                  int row_start, int row_stride, int column_major, float* d_out, cudaStream_t stream, bool timing) {
@@ -179,44 +213,20 @@ int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, in
         rtw::LaunchInfo li{};
         if (ctx->mode == RTW_MODE_CTA_WAVEFRONT && ctx->n_spheres <= rtw::kTileSpheres) {
             RTW_CUDA(ctx, rtw::launch_cta_wavefront_trace(p, ds.num_sms, ctx->blocks_per_sm, stream, &li));
-            launches += li.launches;
         } else if (ctx->mode == RTW_MODE_WAVEFRONT) {
             if (ctx->n_spheres > rtw::kTileSpheres)
                 return fail(ctx, RTW_E_UNSUPPORTED, "RTW_MODE_WAVEFRONT supports at most 1024 spheres; use RTW_MODE_FUSED");
-            // pool size: a whole number of intersect-kernel waves (3 CTAs of 256 lanes per SM), at most ~1M paths
-            const unsigned long long wave = (unsigned long long)ds.num_sms * 3ull * 256ull;
-            unsigned long long want = (p.n_paths + 255ull) & ~255ull;
-            unsigned long long cap_max = ((1ull << 20) / wave) * wave;
-            if (cap_max == 0) cap_max = wave;
-            uint32_t capacity = (uint32_t)(want < cap_max ? want : cap_max);
-            if (capacity < 256u) capacity = 256u;
-            rc = grow(ctx, &ds.d_wf, &ds.wf_cap, rtw::wavefront_bytes(capacity));
-            if (rc) return rc;
             rtw::WavefrontBuffers b;
-            unsigned char* q = ds.d_wf;
-            auto take = [&](size_t bytes) { unsigned char* r = q; q += (bytes + 63) & ~(size_t)63; return r; };
-            b.capacity = capacity;
-            b.ray_o = (float4*)take((size_t)capacity * 16);
-            b.ray_d = (float4*)take((size_t)capacity * 16);
-            b.thr = (double*)take((size_t)capacity * 24);
-            b.pix_local = (uint32_t*)take((size_t)capacity * 4);
-            b.sample = (uint32_t*)take((size_t)capacity * 4);
-            b.pixel = (uint32_t*)take((size_t)capacity * 4);
-            b.depth_left = (int*)take((size_t)capacity * 4);
-            b.hit_t = (float*)take((size_t)capacity * 4);
-            b.hit_k = (int*)take((size_t)capacity * 4);
-            b.alive = (uint32_t*)take((size_t)capacity * 4);
-            for (int l = 0; l < 3; ++l) b.list[l] = (uint32_t*)take((size_t)capacity * 4);
-            b.counts = (unsigned int*)take(64);
+            rc = wavefront_buffers(ctx, ds, p.n_paths, &b);
+            if (rc) return rc;
             RTW_CUDA(ctx, rtw::launch_wavefront_trace(p, b, ds.num_sms, (unsigned int*)(ds.h_counters + 2), stream, &li));
-            launches += li.launches;
         } else {
-        const int rays = ctx->rays_per_lane > 0 ? ctx->rays_per_lane : kDefaultRaysPerLane;
-        const int sweep = ctx->sweep > 0 ? ctx->sweep : kDefaultSweep;
-        const int coop = ctx->coop > 0 ? ctx->coop : kDefaultCoop;
-        RTW_CUDA(ctx, rtw::launch_fused_trace(p, ds.num_sms, ctx->blocks_per_sm, rays, sweep, coop, stream, &li));
-        launches += li.launches;
+            const int rays = ctx->rays_per_lane > 0 ? ctx->rays_per_lane : kDefaultRaysPerLane;
+            const int sweep = ctx->sweep > 0 ? ctx->sweep : kDefaultSweep;
+            const int coop = ctx->coop > 0 ? ctx->coop : kDefaultCoop;
+            RTW_CUDA(ctx, rtw::launch_fused_trace(p, ds.num_sms, ctx->blocks_per_sm, rays, sweep, coop, stream, &li));
         }
+        launches += li.launches;
     }
     if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[1], stream));
     RTW_CUDA(ctx, rtw::launch_resolve(ds.d_accum, W, H, n_rows, row_start, row_stride, spp, std::ldexp(1.0, -fx_bits),

@@ -92,6 +92,12 @@ typedef struct rtw_ctx rtw_ctx;
 #define RTW_OPT_RAYS_PER_LANE 5   /* paths traced concurrently by one lane: 1, 2 or 4 (0 = library default) */
 #define RTW_OPT_SWEEP 6           /* RTW_SWEEP_*: inner-loop variant of the sphere-list sweep          */
 #define RTW_OPT_COOP 7            /* lanes sharing sphere loads in the packed sweep: 1, 2 or 4 (0 = default) */
+#define RTW_OPT_TAIL 8            /* RTW_TAIL_*: layout of the per-bounce work after the sweep (RTW_MODE_FUSED) */
+
+#define RTW_TAIL_DEFAULT 0        /* library default (the fastest measured)                           */
+#define RTW_TAIL_SPLIT 1          /* regenerate / shade each run by the lanes in that state            */
+#define RTW_TAIL_UNIFIED 2        /* one Philox block, cooperative rejection sampling and shared normalize for
+                                     continuing and new paths (packed sweep, 1 path per lane, coop 2 or 4) */
 
 #define RTW_SWEEP_DEFAULT 0       /* library default (the fastest measured)                           */
 #define RTW_SWEEP_BRANCH 1        /* test + immediate root selection under a branch                    */

@@ -44,6 +44,11 @@ RTW_OPT_COLLECT_TIMING = 4
 RTW_OPT_RAYS_PER_LANE = 5
 RTW_OPT_SWEEP = 6
 RTW_OPT_COOP = 7
+RTW_OPT_TAIL = 8
+
+RTW_TAIL_DEFAULT = 0
+RTW_TAIL_SPLIT = 1
+RTW_TAIL_UNIFIED = 2
 
 RTW_SWEEP_DEFAULT = 0
 RTW_SWEEP_BRANCH = 1

@@ -7,9 +7,19 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false
        -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Xptxas -v)
-"$NVCC" "${FLAGS[@]}" -c rtw_kernels.cu -o rtw_kernels.o
-"$NVCC" "${FLAGS[@]}" -c rtw_capi.cu -o rtw_capi.o
-"$NVCC" "${FLAGS[@]}" -c rtw_wavefront.cu -o rtw_wavefront.o
-"$NVCC" "${FLAGS[@]}" -c rtw_cta_wavefront.cu -o rtw_cta_wavefront.o
-"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a rtw_kernels.o rtw_capi.o rtw_wavefront.o rtw_cta_wavefront.o -o librtw_b200.so -lpthread -ldl
+SRCS=(rtw_kernels rtw_fused2 rtw_capi rtw_wavefront rtw_cta_wavefront)
+pids=()
+for s in "${SRCS[@]}"; do
+    "$NVCC" "${FLAGS[@]}" -c "$s.cu" -o "$s.o" > "$s.log" 2>&1 &
+    pids+=($!)
+done
+rc=0
+for i in "${!pids[@]}"; do
+    if ! wait "${pids[$i]}"; then rc=1; echo "== ${SRCS[$i]}.cu failed:"; cat "${SRCS[$i]}.log"; fi
+done
+[ $rc -eq 0 ] || exit 1
+cat ./*.log | grep -E "spill|registers" | sort | uniq -c | sort -rn | head -5 || true
+rm -f ./*.log
+OBJS=("${SRCS[@]/%/.o}")
+"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a "${OBJS[@]}" -o librtw_b200.so -lpthread -ldl
 echo "built $(pwd)/librtw_b200.so"

@@ -24,6 +24,9 @@ struct DeviceState {
     // scene
     float4* d_geom = nullptr;
     float4* d_geom_pairs = nullptr;
+    float4* d_geom_perm[2] = {nullptr, nullptr};  // RTW_TAIL_UNIFIED: lane-order AoS copies for coop = 2, 4 (lists <= 1024)
+    float* d_uv = nullptr;                         // u_tab (W) then v_tab (H)
+    size_t uv_cap = 0;
     float4* d_mat = nullptr;
     uint32_t* d_kind = nullptr;
     size_t scene_cap = 0;
@@ -59,6 +62,7 @@ struct rtw_ctx {
     int rays_per_lane = 0;  // 0 = default
     int sweep = 0;          // 0 = default
     int coop = 0;           // 0 = default
+    int tail = 0;           // RTW_TAIL_*; 0 = default
     int blocks_per_sm = 0;
     int collect_timing = 1;
 };
@@ -69,6 +73,7 @@ namespace {
 constexpr int kDefaultRaysPerLane = 1;
 constexpr int kDefaultSweep = RTW_SWEEP_PACKED;
 constexpr int kDefaultCoop = 2;
+constexpr int kDefaultTail = RTW_TAIL_UNIFIED;
 
 int fail(rtw_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg;
@@ -200,6 +205,9 @@ int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, in
         p.cam = to_dev_camera(cam);
         p.geom = ds.d_geom;
         p.geom_pairs = ds.d_geom_pairs;
+        p.geom_perm = nullptr;
+        p.u_tab = p.v_tab = nullptr;
+        p.div_spp = p.div_w = rtw::MagicDiv{0u, 0u, 0u};
         p.mat = ds.d_mat;
         p.kind = ds.d_kind;
         p.n_spheres = ctx->n_spheres;
@@ -224,7 +232,22 @@ int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, in
             const int rays = ctx->rays_per_lane > 0 ? ctx->rays_per_lane : kDefaultRaysPerLane;
             const int sweep = ctx->sweep > 0 ? ctx->sweep : kDefaultSweep;
             const int coop = ctx->coop > 0 ? ctx->coop : kDefaultCoop;
-            RTW_CUDA(ctx, rtw::launch_fused_trace(p, ds.num_sms, ctx->blocks_per_sm, rays, sweep, coop, stream, &li));
+            const int tail = ctx->tail > 0 ? ctx->tail : kDefaultTail;
+            // the unified tail exists for the default sweep family: packed, one path per lane, 2 or 4 cooperating lanes
+            if (tail == RTW_TAIL_UNIFIED && rays == 1 && sweep == RTW_SWEEP_PACKED && (coop == 2 || coop == 4)) {
+                rc = grow(ctx, &ds.d_uv, &ds.uv_cap, (size_t)W + (size_t)H);
+                if (rc) return rc;
+                RTW_CUDA(ctx, rtw::launch_uv_tables(W, H, ds.d_uv, ds.d_uv + W, stream));
+                launches += 1;
+                p.geom_perm = ds.d_geom_perm[coop == 2 ? 0 : 1];
+                p.u_tab = ds.d_uv;
+                p.v_tab = ds.d_uv + W;
+                p.div_spp = rtw::make_magic_div((uint32_t)spp);
+                p.div_w = rtw::make_magic_div((uint32_t)W);
+                RTW_CUDA(ctx, rtw::launch_fused_trace2(p, ds.num_sms, ctx->blocks_per_sm, coop, stream, &li));
+            } else {
+                RTW_CUDA(ctx, rtw::launch_fused_trace(p, ds.num_sms, ctx->blocks_per_sm, rays, sweep, coop, stream, &li));
+            }
         }
         launches += li.launches;
     }
@@ -268,17 +291,36 @@ int set_scene_locked(rtw_ctx* ctx, const float* geom4, const float* mat4, const 
         dst[4] = geom4[4 * (size_t)i + 2];
         dst[6] = geom4[4 * (size_t)i + 3];
     }
+    // RTW_TAIL_UNIFIED: copies of the list in the order the lanes of a cooperating group meet the spheres
+    // (single-tile lists only): entry (c*coop + h)*32 + j = sphere c*32*coop + 2*((j>>1)*coop + h) + (j&1)
+    std::vector<float> perm[2];
+    size_t perm_entries[2] = {0, 0};
+    if (n > 0 && n <= rtw::kTileSpheres) {
+        for (int v = 0; v < 2; ++v) {
+            const uint32_t coop = v == 0 ? 2u : 4u, super = 32u * coop;
+            const uint32_t nsc = (n + super - 1u) / super;
+            perm_entries[v] = (size_t)nsc * super;
+            perm[v].assign(perm_entries[v] * 4u, 0.0f);
+            for (uint32_t kl = 0; kl < n; ++kl) {
+                const uint32_t c = kl / super, within = kl % super, pr = within >> 1, half = within & 1u;
+                const uint32_t h = pr % coop, i = pr / coop, j = 2u * i + half;
+                std::memcpy(perm[v].data() + ((size_t)(c * coop + h) * 32u + j) * 4u, geom4 + 4 * (size_t)kl, 16);
+            }
+        }
+    }
     for (auto& ds : ctx->dev) {
         RTW_CUDA(ctx, cudaSetDevice(ds.device));
         if (n > ds.scene_cap || !ds.d_geom) {
             if (ds.d_geom) cudaFree(ds.d_geom);
             if (ds.d_geom_pairs) cudaFree(ds.d_geom_pairs);
+            for (auto& q : ds.d_geom_perm) { if (q) cudaFree(q); q = nullptr; }
             if (ds.d_mat) cudaFree(ds.d_mat);
             if (ds.d_kind) cudaFree(ds.d_kind);
             ds.d_geom = nullptr; ds.d_geom_pairs = nullptr; ds.d_mat = nullptr; ds.d_kind = nullptr; ds.scene_cap = 0;
             size_t cap = n ? n : 1;
             RTW_CUDA(ctx, cudaMalloc((void**)&ds.d_geom, cap * sizeof(float4)));
             RTW_CUDA(ctx, cudaMalloc((void**)&ds.d_geom_pairs, (cap + 1) * sizeof(float4)));
+            for (auto& q : ds.d_geom_perm) RTW_CUDA(ctx, cudaMalloc((void**)&q, (cap + 128) * sizeof(float4)));
             RTW_CUDA(ctx, cudaMalloc((void**)&ds.d_mat, cap * sizeof(float4)));
             RTW_CUDA(ctx, cudaMalloc((void**)&ds.d_kind, cap * sizeof(uint32_t)));
             ds.scene_cap = cap;
@@ -288,6 +330,9 @@ int set_scene_locked(rtw_ctx* ctx, const float* geom4, const float* mat4, const 
             RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_geom_pairs, pairs.data(), pairs.size() * sizeof(float), cudaMemcpyHostToDevice, ds.stream));
             RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_mat, mat4, (size_t)n * 16, cudaMemcpyHostToDevice, ds.stream));
             RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_kind, kind, (size_t)n * 4, cudaMemcpyHostToDevice, ds.stream));
+            for (int v = 0; v < 2; ++v)
+                if (perm_entries[v])
+                    RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_geom_perm[v], perm[v].data(), perm_entries[v] * 16, cudaMemcpyHostToDevice, ds.stream));
         }
     }
     for (auto& ds : ctx->dev) {
@@ -467,6 +512,7 @@ int rtw_destroy(rtw_ctx* ctx) {
         if (cudaSetDevice(ds.device) != cudaSuccess) continue;
         if (ds.stream) cudaStreamSynchronize(ds.stream);
         cudaFree(ds.d_geom); cudaFree(ds.d_geom_pairs); cudaFree(ds.d_mat); cudaFree(ds.d_kind);
+        cudaFree(ds.d_geom_perm[0]); cudaFree(ds.d_geom_perm[1]); cudaFree(ds.d_uv);
         cudaFree(ds.d_accum); cudaFree(ds.d_counters); cudaFree(ds.d_tile);
         cudaFree(ds.d_gather); cudaFree(ds.d_image); cudaFree(ds.d_scratch); cudaFree(ds.d_wf);
         if (ds.h_counters) cudaFreeHost(ds.h_counters);
@@ -504,6 +550,11 @@ int rtw_set_option(rtw_ctx* ctx, int option, int64_t value) {
         case RTW_OPT_SWEEP:
             if (value < 0 || value > RTW_SWEEP_PACKED) return fail(ctx, RTW_E_INVALID_ARG, "unknown sweep variant");
             ctx->sweep = (int)value;
+            return RTW_OK;
+        case RTW_OPT_TAIL:
+            if (value != RTW_TAIL_DEFAULT && value != RTW_TAIL_SPLIT && value != RTW_TAIL_UNIFIED)
+                return fail(ctx, RTW_E_INVALID_ARG, "unknown tail variant");
+            ctx->tail = (int)value;
             return RTW_OK;
         case RTW_OPT_BLOCKS_PER_SM:
             if (value < 0 || value > 32) return fail(ctx, RTW_E_INVALID_ARG, "blocks_per_sm must be in 0..32");

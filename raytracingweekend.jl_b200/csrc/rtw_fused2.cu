@@ -1,0 +1,526 @@
+// rtw_fused2.cu -- RTW_TAIL_UNIFIED: the persistent fused trace kernel with a warp-converged tail.
+//
+// Same path, same bits as fused_trace_kernel (rtw_kernels.cu); what differs is how the work AFTER the sphere-list
+// sweep is laid out.  The roofline of this kernel is FP32 issue slots, so every warp instruction that is not one
+// of the 11 FP32 lane-ops of a ray-sphere test costs wall time at the rate of one slot per instruction, whatever
+// the number of lanes it serves.  After the sweep a warp holds lanes in different states (path ended / scatters
+// on Lambertian, Metal, Dielectric / needs a new primary ray), and the first kernel ran each state's code at
+// 8-10 of 32 lanes.  Here the states share their expensive pieces:
+//   * the lanes whose path ended take their next path ticket BEFORE the random draws, so that ONE Philox block 0
+//     serves the scatter of the continuing lanes (src/material.jl) and the primary ray of the new lanes
+//     (src/render.jl:30-37, src/camera.jl:43-48);
+//   * the rejection loops (src/rand.jl:15-22 ball, :31-38 disk) run warp-cooperatively: the lanes that still need
+//     a sample publish their stream address in shared memory and ALL 32 lanes evaluate the following attempts for
+//     them (the stream is addressed, not sequential, so attempt a of a path can be computed by any lane); a lane
+//     takes the first accepted attempt in stream order, so the result is the same as the sequential loop's;
+//   * one normalize() instance serves unit(ball sample) and the primary-ray direction, a second one serves the
+//     scattered directions of all three materials;
+//   * u = T(j/W), v = T((H-i)/H) (src/render.jl:26-27) come from tables filled once per render, ticket -> (pixel,
+//     sample) uses multiply-shift division;
+//   * candidate resolution after the sweep reads the spheres from a copy laid out in the order a lane meets them
+//     (one LEA + LDS.128 per candidate), keeps (t, position) only and decodes the list index once.
+#include "rtw_kernels.h"
+#include "rtw_sweep.cuh"
+
+namespace rtw {
+
+namespace {
+
+__device__ __forceinline__ uint32_t magic_div(uint32_t n, const MagicDiv k) {
+    const uint32_t t = __umulhi(k.m, n);
+    return (t + ((n - t) >> k.sh1)) >> k.sh2;
+}
+
+__device__ __forceinline__ uint32_t bfind_u32(uint32_t x) {  // position of the highest set bit (x != 0)
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
+
+// random_between(-1, 1) of the word's uniform (src/rand.jl:24): 2*(k*2^-23) - 1 = k*2^-22 - 1, exact either way
+__device__ __forceinline__ float pm1x(uint32_t w) { return fmaf((float)(w >> 9), 2.384185791015625e-07f, -1.0f); }
+
+// ---- candidate resolution over the permuted AoS copy ----------------------------------------------------------
+// aos_perm[(c*kCoop + h)*32 + j] = the sphere that lane h of a group tests as its j-th test of super-chunk c, i.e.
+// list index c*32*kCoop + 2*((j>>1)*kCoop + h) + (j&1).  Mask bit (31 - j) of word (c, slot) clear = candidate.
+// Candidates are visited in list order per slot, so ties in t go to the later sphere (src/hit.jl:24-26,44-46).
+__device__ __forceinline__ float4 lds128(uint32_t addr) {  // 32-bit shared-window address
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");  // ordered after this thread's mask stores
+    return v;
+}
+
+template <int NS, int kCoop, int kBlock>
+__device__ __forceinline__ void walk_candidates_perm(const float4* __restrict__ aos_perm, uint32_t coop_h,
+                                                     const uint32_t* __restrict__ s_mask, const f3 (&o)[NS],
+                                                     const f3 (&d)[NS], const bool (&alive)[NS],
+                                                     const uint32_t (&summary)[NS], float (&best_t)[NS],
+                                                     int (&best_k)[NS]) {
+    const float tmin = 1e-4f;  // T(1e-4), src/ray_color.jl:19
+    // 32-bit shared addresses: of entry 31 of this lane's run in super-chunk 0, and of this lane's mask word 0
+    const uint32_t a_lane = smem_u32(aos_perm) + (coop_h * 32u + 31u) * 16u;
+    const uint32_t m_lane = smem_u32(s_mask);
+#pragma unroll
+    for (int r = 0; r < NS; ++r) {
+        uint32_t sum = alive[r] ? summary[r] : 0u;
+        uint32_t cand = 0u;
+        uint32_t a31 = 0u;   // address of test j = 0's partner at bit 31: test j = 31 - p sits at a31 - 16*p
+        uint32_t code31 = 0u;  // (c*kCoop + h)*32 + 31: position code of bit p is code31 - p
+        float bt = __int_as_float(0x7f800000);
+        uint32_t bcode = 0xffffffffu;
+        const float ox = o[r].x, oy = o[r].y, oz = o[r].z, dx = d[r].x, dy = d[r].y, dz = d[r].z;
+        for (;;) {
+            if (cand == 0u) {
+                if (sum == 0u) break;
+                const uint32_t c = (uint32_t)__ffs((int)sum) - 1u;
+                sum &= sum - 1u;
+                cand = ~lds32(m_lane + (c * NS + r) * (kBlock * 4u));  // != 0: summary bits mark words with a candidate
+                a31 = a_lane + c * (kCoop * 32u * 16u);
+                code31 = (c * kCoop + coop_h) * 32u + 31u;
+            }
+            const uint32_t p = bfind_u32(cand);
+            cand &= (1u << p) - 1u;  // p is the highest set bit
+            const float4 s = lds128(a31 - 16u * p);
+            // scalar redo of src/hit.jl:13-18: bit-identical to the packed values of the sweep
+            const float ocx = ox - s.x, ocy = oy - s.y, ocz = oz - s.z;
+            const float hb = fmaf(ocz, dz, fmaf(ocy, dy, ocx * dx));
+            const float cq = fmaf(-s.w, s.w, fmaf(ocz, ocz, fmaf(ocy, ocy, ocx * ocx)));
+            // Sphere entirely behind the origin (half_b > 0 and origin outside): sqrt(disc) <= half_b in IEEE
+            // arithmetic, so both roots are <= 0 < tmin and src/hit.jl:24-28 rejects them -- skip the square root.
+            if (hb > 0.0f && cq > 0.0f) continue;
+            const float sq = __fsqrt_rn(fmaf(hb, hb, -cq));
+            const float r1 = -hb - sq, r2 = -hb + sq;            // src/hit.jl:23, 25
+            const bool bad1 = r1 < tmin || bt < r1;              // src/hit.jl:24
+            const bool bad2 = r2 < tmin || bt < r2;              // src/hit.jl:26
+            if (!(bad1 && bad2)) {
+                bt = bad1 ? r2 : r1;
+                bcode = code31 - p;  // (c*kCoop + h)*32 + j
+            }
+        }
+        best_t[r] = bt;
+        if (bcode != 0xffffffffu) {
+            const uint32_t j = bcode & 31u, cq2 = bcode >> 5;  // cq2 = c*kCoop + h
+            const uint32_t c = cq2 / (uint32_t)kCoop;
+            best_k[r] = (int)(c * (32u * kCoop) + 2u * ((j >> 1) * kCoop + coop_h) + (j & 1u));
+        } else {
+            best_k[r] = -1;
+        }
+    }
+}
+
+// closest hit of one ray per lane over a single resident tile: ray exchange inside the lane group, packed mask
+// sweep, candidate walk over the permuted copy, merge of the partial results (list-order tie rule)
+template <int kCoop, int kBlock>
+__device__ __forceinline__ void closest_hit_single_tile(const float4* __restrict__ tile,
+                                                        const float4* __restrict__ aos_perm, uint32_t count,
+                                                        uint32_t* __restrict__ s_mask, const f3 o, const f3 d,
+                                                        const bool alive, float& best_t, int& best_k) {
+    const uint32_t h = threadIdx.x & (kCoop - 1);
+    f3 so[kCoop], sd[kCoop];
+    bool sa[kCoop];
+    float bt[kCoop];
+    int bk[kCoop];
+    uint32_t summary[kCoop];
+#pragma unroll
+    for (int q = 0; q < kCoop; ++q) {  // slot q holds the ray of lane (lane ^ q)
+        if (q == 0) {
+            so[0] = o; sd[0] = d; sa[0] = alive;
+        } else {
+            so[q] = mk3(__shfl_xor_sync(kFullMask, o.x, q), __shfl_xor_sync(kFullMask, o.y, q),
+                        __shfl_xor_sync(kFullMask, o.z, q));
+            sd[q] = mk3(__shfl_xor_sync(kFullMask, d.x, q), __shfl_xor_sync(kFullMask, d.y, q),
+                        __shfl_xor_sync(kFullMask, d.z, q));
+            sa[q] = __shfl_xor_sync(kFullMask, alive ? 1 : 0, q) != 0;
+        }
+    }
+    sweep_masks_packed<kCoop, kCoop, kBlock>(tile, count, h, s_mask, so, sd, summary);
+    walk_candidates_perm<kCoop, kCoop, kBlock>(aos_perm, h, s_mask, so, sd, sa, summary, bt, bk);
+    best_t = bt[0];
+    best_k = bk[0];
+#pragma unroll
+    for (int q = 1; q < kCoop; ++q) {  // lane ^ q holds, in ITS slot q, the partial result for my ray
+        const float pt = __shfl_xor_sync(kFullMask, bt[q], q);
+        const int pk = __shfl_xor_sync(kFullMask, bk[q], q);
+        if (pk >= 0 && (best_k < 0 || pt < best_t || (pt == best_t && pk > best_k))) {
+            best_t = pt;
+            best_k = pk;
+        }
+    }
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------------------
+template <bool kMulti, int kCoop>
+__global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __grid_constant__ TraceParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ __align__(16) uint4 s_coop[kTraceBlock / 32][32];  // rejection-sampling requests of a warp
+    const uint32_t n = P.n_spheres;
+    const float4* __restrict__ g_src = P.geom_pairs;
+    const uint32_t n_stage = (n + 1u) & ~1u;
+    const uint32_t n_tiles = kMulti ? (n + kTileSpheres - 1u) / kTileSpheres : 1u;
+    constexpr uint32_t kGran = 32u * kCoop;
+    const uint32_t tile_cap = kMulti ? kTileSpheres : ((n + kGran - 1u) / kGran) * kGran;
+    float4* s_tile0 = reinterpret_cast<float4*>(smem_raw);
+    float4* s_tile1 = s_tile0 + tile_cap;  // kMulti: second streaming buffer; else: permuted AoS copy of the list
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tile0 + 2u * tile_cap) + threadIdx.x;
+
+    for (uint32_t i = threadIdx.x; i < 2u * tile_cap; i += kTraceBlock) s_tile0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    uint32_t bar_phase0 = 0u, bar_phase1 = 0u;
+    if (!kMulti) {
+        if (threadIdx.x == 0 && n > 0u) {
+            mbar_arrive_expect_tx(&s_bar[0], n_stage * 16u + tile_cap * 16u);
+            tma_bulk_g2s(s_tile0, g_src, n_stage * 16u, &s_bar[0]);
+            tma_bulk_g2s(s_tile1, P.geom_perm, tile_cap * 16u, &s_bar[0]);
+        }
+        if (n > 0u) mbar_wait(&s_bar[0], 0u);
+    }
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t k0 = P.key0, k1 = P.key1;
+    uint4* const coop_slot = s_coop[threadIdx.x >> 5];
+
+    // path state of the lane
+    f3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 1.f, 0.f);
+    double thr_r = 1.0, thr_g = 1.0, thr_b = 1.0;  // product of attenuations so far (Float64, as the reference promotes)
+    uint32_t pix_local = 0u, pixel = 0u, sample = 0u, nhits = 0u;
+    bool alive = false, done = false;
+    float best_t = __int_as_float(0x7f800000);
+    int best_k = -1;
+    uint32_t seg_count = 0;
+    unsigned long long pool_next = 0, pool_end = 0;  // warp-level ticket pool (uniform)
+    bool exhausted = false;
+
+    for (;;) {
+        // ------------------------------------------------------------ classify + accumulate the ended paths
+        bool cont = false;
+        if (alive) {
+            seg_count += 1;
+            if (best_k < 0) {  // miss: sky (src/ray_color.jl:36), path ends
+                double sr, sg, sb;
+                skycolor(d, sr, sg, sb);
+                // accumulate (src/render.jl:38): order-independent fixed-point atomics
+                unsigned long long* a = P.accum + (unsigned long long)pix_local * 4ull;
+                atomicAdd(a + 0, (unsigned long long)__double2ll_rn(__dmul_rn(thr_r, sr) * P.fx_scale));
+                atomicAdd(a + 1, (unsigned long long)__double2ll_rn(__dmul_rn(thr_g, sg) * P.fx_scale));
+                atomicAdd(a + 2, (unsigned long long)__double2ll_rn(__dmul_rn(thr_b, sb) * P.fx_scale));
+                alive = false;
+            } else if (++nhits == (uint32_t)P.max_depth) {
+                alive = false;  // the next ray_color call returns black (src/ray_color.jl:15-17): adds nothing
+            } else {
+                cont = true;
+            }
+        }
+        uint32_t kind = 0u;
+        if (cont) kind = __ldg(P.kind + best_k);
+
+        // ------------------------------------------------------------ regenerate: idle lanes take the next path
+        bool newp = false;
+        unsigned long long ticket = 0;
+        {
+            bool want = !alive && !done;
+            unsigned pending = __ballot_sync(kFullMask, want);
+            while (pending) {
+                if (exhausted) {
+                    if (want) { done = true; want = false; }
+                    break;
+                }
+                if (pool_next >= pool_end) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(P.counters, (unsigned long long)kPoolChunk);
+                    base = __shfl_sync(kFullMask, base, 0);
+                    if (base >= P.n_paths) { exhausted = true; continue; }
+                    pool_next = base;
+                    pool_end = base + kPoolChunk < P.n_paths ? base + kPoolChunk : P.n_paths;
+                }
+                const unsigned avail = (unsigned)(pool_end - pool_next);
+                const unsigned rank = __popc(pending & lt_mask);
+                if (want && rank < avail) { ticket = pool_next + rank; want = false; newp = true; }
+                const unsigned npend = __popc(pending);
+                pool_next += npend < avail ? npend : avail;
+                pending = __ballot_sync(kFullMask, want);
+            }
+        }
+        float su = 0.f, sv = 0.f;
+        uint32_t s0 = 0u, pl = 0u;
+        if (newp) {
+            // ticket -> (pixel, sample): consecutive tickets are consecutive samples of one pixel
+            if ((P.n_paths >> 32) == 0ull) {
+                pl = magic_div((uint32_t)ticket, P.div_spp);
+                s0 = (uint32_t)ticket - pl * (uint32_t)P.spp;
+            } else {
+                const unsigned long long q = ticket / (unsigned)P.spp;
+                pl = (uint32_t)q;
+                s0 = (uint32_t)(ticket - q * (unsigned)P.spp);
+            }
+            const uint32_t row_local = magic_div(pl, P.div_w);
+            const uint32_t col = pl - row_local * (uint32_t)P.W;
+            const uint32_t i0 = (uint32_t)P.row_start + row_local * (uint32_t)P.row_stride;
+            su = __ldg(P.u_tab + col);  // T(j/W), src/render.jl:26
+            sv = __ldg(P.v_tab + i0);   // T((H-i)/H), src/render.jl:27
+            pixel = i0 * (uint32_t)P.W + col;
+            sample = s0;
+        }
+        if (kMulti) {
+            if (__syncthreads_or((cont || newp) ? 1 : 0) == 0) break;  // also: everyone is done with both tile buffers
+        } else {
+            if (__ballot_sync(kFullMask, cont || newp) == 0u) break;
+        }
+
+        // ------------------------------------------------------------ block 0 of the event, for every lane at once
+        // continuing lanes: event = index of this hit (scatter draws); new lanes: event 0 (primary-ray draws)
+        const uint32_t ev = cont ? nhits : 0u;
+        const u32x4 b0 = philox_block(PathRng{sample, pixel}, ev, 0u, k0, k1);
+        float px = pm1x(b0.w0), py = pm1x(b0.w1), pz = pm1x(b0.w2);
+        const float pw = pm1x(b0.w3);
+        const bool ball = cont && kind != 2u;  // Lambertian and Metal draw a unit vector (Metal even when fuzz == 0)
+        float js = su, jt = sv;                // new lanes: jittered screen coordinates (src/render.jl:30-36)
+        float coin = 0.f;                      // dielectric coin, draw 3 of the event (src/material.jl:47)
+        bool need;
+        {
+            const float q01 = fmaf(py, py, px * px);
+            const float qball = fmaf(pz, pz, q01);
+            const float q23 = fmaf(pw, pw, pz * pz);
+            if (newp) {
+                if (s0 != 0u) {  // du = draw 0, dv = draw 1; the first sample is centred
+                    js = su + __fdiv_rn(u01(b0.w0), (float)P.W);
+                    jt = sv + __fdiv_rn(u01(b0.w1), (float)P.H);
+                }
+                px = pz;  // disk attempt 0 = draws 2, 3 (src/rand.jl:31-38; always drawn, src/camera.jl:44)
+                py = pw;
+            } else {
+                coin = u01(b0.w3);
+            }
+            need = ball ? !(qball <= 1.0f) : (newp ? !(q23 <= 1.0f) : false);
+        }
+        // ------------------------------------------------------------ cooperative rejection sampling
+        // attempt a >= 1 of the ball  = words 0..2 of block a of the event (src/rand.jl:15-22)
+        // attempts 2a-1, 2a of the disk = words (0,1), (2,3) of block a of event 0 (src/rand.jl:31-38)
+        {
+            unsigned needm = __ballot_sync(kFullMask, need);
+            uint32_t blk = 1u;  // next unevaluated block; uniform: every needy lane has failed the same attempts
+            while (needm) {
+                const uint32_t cnt = (uint32_t)__popc(needm);
+                const uint32_t sh = cnt <= 1u ? 5u : (uint32_t)__clz((int)(cnt - 1u)) - 27u;  // 2^sh helpers per lane
+                const uint32_t rank = (uint32_t)__popc(needm & lt_mask);
+                if (need) coop_slot[rank] = make_uint4(sample, pixel, ev | (newp ? 0x80000000u : 0u), 0u);
+                __syncwarp();
+                const uint32_t hq = lane >> sh, ha = lane & ((1u << sh) - 1u);
+                const uint4 tsk = coop_slot[hq < cnt ? hq : 0u];
+                const u32x4 hb = philox_block(PathRng{tsk.x, tsk.y}, tsk.z & 0x7fffffffu, blk + ha, k0, k1);
+                float hx = pm1x(hb.w0), hy = pm1x(hb.w1);
+                const float hz = pm1x(hb.w2), hw = pm1x(hb.w3);
+                const float q01 = fmaf(hy, hy, hx * hx);
+                const float qball = fmaf(hz, hz, q01);
+                const float q23 = fmaf(hw, hw, hz * hz);
+                const bool is_disk = (tsk.z >> 31) != 0u;
+                const bool ok01 = q01 <= 1.0f;
+                const bool ok = hq < cnt && (is_disk ? (ok01 || q23 <= 1.0f) : (qball <= 1.0f));
+                if (is_disk && !ok01) { hx = hz; hy = hw; }
+                const unsigned okm = __ballot_sync(kFullMask, ok);
+                const uint32_t wmask = sh >= 5u ? 0xffffffffu : ((1u << (1u << sh)) - 1u);
+                const uint32_t mine = need ? ((okm >> (rank << sh)) & wmask) : 0u;
+                const uint32_t src = mine ? (rank << sh) + (uint32_t)__ffs((int)mine) - 1u : lane;
+                const float gx = __shfl_sync(kFullMask, hx, src);
+                const float gy = __shfl_sync(kFullMask, hy, src);
+                const float gz = __shfl_sync(kFullMask, hz, src);
+                if (mine) { px = gx; py = gy; pz = gz; need = false; }
+                blk += 1u << sh;
+                needm = __ballot_sync(kFullMask, need);
+            }
+        }
+
+        // ------------------------------------------------------------ new lanes: get_ray (src/camera.jl:43-48)
+        f3 v1 = mk3(px, py, pz);  // continuing Lambertian/Metal lanes: the point in the unit ball
+        f3 o_new = o;
+        if (newp) {
+            const DevCamera& c = P.cam;
+            const float rx = c.lens_radius * px, ry = c.lens_radius * py;
+            const f3 off = mk3(fmaf(c.v.x, ry, c.u.x * rx), fmaf(c.v.y, ry, c.u.y * rx), fmaf(c.v.z, ry, c.u.z * rx));
+            o_new = mk3(c.origin.x + off.x, c.origin.y + off.y, c.origin.z + off.z);
+            v1.x = fmaf(jt, c.vertical.x, fmaf(js, c.horizontal.x, c.llc.x)) - c.origin.x - off.x;
+            v1.y = fmaf(jt, c.vertical.y, fmaf(js, c.horizontal.y, c.llc.y)) - c.origin.y - off.y;
+            v1.z = fmaf(jt, c.vertical.z, fmaf(js, c.horizontal.z, c.llc.z)) - c.origin.z - off.z;
+        }
+        const f3 n1 = normalize3(v1);  // unit(ball sample) | primary direction: one instance for both
+
+        // ------------------------------------------------------------ continuing lanes: HitRecord + scatter
+        f3 v2 = mk3(1.f, 0.f, 0.f);  // direction before the final normalize
+        f3 alt = v2;                 // direction used as is (near-zero Lambertian, reflecting Dielectric)
+        bool use_alt = false;
+        if (cont) {
+            const float4 g = __ldg(P.geom + best_k);
+            const float4 m = __ldg(P.mat + best_k);
+            const f3 p = mk3(fmaf(best_t, d.x, o.x), fmaf(best_t, d.y, o.y), fmaf(best_t, d.z, o.z));   // hit.jl:3
+            const f3 on = mk3(__fdiv_rn(p.x - g.x, g.w), __fdiv_rn(p.y - g.y, g.w), __fdiv_rn(p.z - g.z, g.w));  // hit.jl:33
+            const bool front = dot3(d, on) < 0.0f;                                                    // hit.jl:7
+            const f3 nn = front ? on : mk3(-on.x, -on.y, -on.z);                                      // hit.jl:8
+            if (kind == 0u) {  // Lambertian, material.jl:13-23
+                v2 = mk3(nn.x + n1.x, nn.y + n1.y, nn.z + n1.z);
+                // near_zero: squared length (Float32) promoted and compared with the Float64 literal 1e-5, vec.jl:20
+                use_alt = (double)dot3(v2, v2) < 1e-5;
+                alt = nn;
+            } else if (kind == 1u) {  // Metal, material.jl:31-34; never absorbs (structs.jl:43)
+                const f3 refl = reflect3(d, nn);
+                v2 = mk3(fmaf(m.w, n1.x, refl.x), fmaf(m.w, n1.y, refl.y), fmaf(m.w, n1.z, refl.z));
+            } else {  // Dielectric, material.jl:41-53
+                const float ratio = front ? __fdiv_rn(1.0f, m.w) : m.w;
+                const float cos_t = fminf(-dot3(d, nn), 1.0f);
+                const float sin_t = __fsqrt_rn(fmaf(-cos_t, cos_t, 1.0f));
+                // `||` short-circuits (material.jl:47): the coin is ignored on total internal reflection
+                if (ratio * sin_t > 1.0f || reflectance(cos_t, ratio) > coin) {
+                    use_alt = true;
+                    alt = reflect3(d, nn);  // not re-normalised, material.jl:48
+                } else {  // refract, light.jl:12-17
+                    const f3 perp = mk3(ratio * fmaf(cos_t, nn.x, d.x), ratio * fmaf(cos_t, nn.y, d.y),
+                                        ratio * fmaf(cos_t, nn.z, d.z));
+                    const float s = __fsqrt_rn(fabsf(1.0f - dot3(perp, perp)));
+                    v2 = mk3(fmaf(-s, nn.x, perp.x), fmaf(-s, nn.y, perp.y), fmaf(-s, nn.z, perp.z));
+                }
+            }
+            if (kind != 2u) {  // attenuation = albedo (Dielectric: (1,1,1), an exact no-op)
+                thr_r = __dmul_rn(thr_r, (double)m.x);
+                thr_g = __dmul_rn(thr_g, (double)m.y);
+                thr_b = __dmul_rn(thr_b, (double)m.z);
+            }
+            o = p;
+        }
+        const f3 n2 = normalize3(v2);  // one instance for the three materials
+        if (cont) {
+            d = use_alt ? alt : n2;
+        } else if (newp) {
+            o = o_new;
+            d = n1;
+            thr_r = thr_g = thr_b = 1.0;
+            nhits = 0u;
+            pix_local = pl;
+            alive = true;
+        }
+
+        // ------------------------------------------------------------ intersect: closest hit over the list
+        best_t = __int_as_float(0x7f800000);  // typemax(T) = Inf, src/ray_color.jl:19
+        best_k = -1;
+        if (!kMulti) {
+            closest_hit_single_tile<kCoop, kTraceBlock>(s_tile0, s_tile1, n, s_mask, o, d, alive, best_t, best_k);
+        } else {
+            f3 oa[1] = {o}, da[1] = {d};
+            bool aa[1] = {alive};
+            float bta[1] = {best_t};
+            int bka[1] = {best_k};
+            if (threadIdx.x == 0) {  // prologue: tile 0 -> buffer 0
+                const uint32_t cnt = n_stage < kTileSpheres ? n_stage : kTileSpheres;
+                mbar_arrive_expect_tx(&s_bar[0], cnt * 16u);
+                tma_bulk_g2s(s_tile0, g_src, cnt * 16u, &s_bar[0]);
+            }
+            for (uint32_t t = 0; t < n_tiles; ++t) {
+                const uint32_t base = t * kTileSpheres;
+                const uint32_t cnt = n - base < kTileSpheres ? n - base : kTileSpheres;
+                if (threadIdx.x == 0 && t + 1u < n_tiles) {  // prefetch tile t+1 into the other buffer
+                    const uint32_t nb = base + kTileSpheres;
+                    const uint32_t ncnt = n_stage - nb < kTileSpheres ? n_stage - nb : kTileSpheres;
+                    unsigned long long* bar = &s_bar[(t + 1u) & 1u];
+                    mbar_arrive_expect_tx(bar, ncnt * 16u);
+                    tma_bulk_g2s((t & 1u) ? s_tile0 : s_tile1, g_src + nb, ncnt * 16u, bar);
+                }
+                const float4* tile = (t & 1u) ? s_tile1 : s_tile0;
+                if (t & 1u) { mbar_wait(&s_bar[1], bar_phase1); bar_phase1 ^= 1u; }
+                else { mbar_wait(&s_bar[0], bar_phase0); bar_phase0 ^= 1u; }
+                sweep_tile<1, kSweepPacked, kCoop, kTraceBlock>(tile, nullptr, cnt, base, s_mask, oa, da, aa, bta, bka);
+                __syncthreads();  // the buffer may be overwritten by the prefetch issued in the next iteration
+            }
+            best_t = bta[0];
+            best_k = bka[0];
+        }
+    }
+    // ray-segment statistics: one atomic per warp
+    for (int off = 16; off > 0; off >>= 1) seg_count += __shfl_xor_sync(kFullMask, seg_count, off);
+    if (lane == 0 && seg_count) atomicAdd(P.counters + 1, (unsigned long long)seg_count);
+}
+
+// u_tab[col] = T((col+1)/W), v_tab[i0] = T((H-1-i0)/H) (src/render.jl:26-27): the quotient is formed in Float64 and
+// rounded to Float32 by the reference; both operands are integers < 2^24, so the correctly rounded Float32 quotient
+// is the same value (rounding through a format with >= 2*24+2 bits is innocuous for division).
+__global__ void __launch_bounds__(256) uv_table_kernel(int W, int H, float* __restrict__ u_tab,
+                                                       float* __restrict__ v_tab) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < W) u_tab[t] = __fdiv_rn((float)(t + 1), (float)W);
+    if (t < H) v_tab[t] = __fdiv_rn((float)(H - 1 - t), (float)H);
+}
+
+template <bool kMulti, int kCoop>
+cudaError_t launch_variant2(const TraceParams& p, int num_sms, int blocks_per_sm_override, cudaStream_t stream,
+                            LaunchInfo* info) {
+    auto kern = fused_trace2_kernel<kMulti, kCoop>;
+    constexpr uint32_t kGran = 32u * kCoop;
+    const uint32_t tile_cap = kMulti ? kTileSpheres : ((p.n_spheres + kGran - 1u) / kGran) * kGran;
+    const uint32_t chunks = tile_cap / 32u;  // mask words per lane: (tile_cap / kGran) super-chunks x kCoop slots
+    const int smem = (int)(2u * tile_cap * 16u + chunks * kTraceBlock * 4u);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTraceBlock, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    if (blocks_per_sm_override > 0 && blocks_per_sm_override < per_sm) per_sm = blocks_per_sm_override;
+    long long grid = (long long)num_sms * per_sm;  // persistent grid: every CTA is resident
+    const long long max_useful = (long long)((p.n_paths + (unsigned long long)kTraceBlock - 1ull) /
+                                             (unsigned long long)kTraceBlock);
+    if (grid > max_useful) grid = max_useful;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, kTraceBlock, smem, stream>>>(p);
+    if (info) {
+        info->grid = (int)grid;
+        info->block = kTraceBlock;
+        info->smem_bytes = smem;
+        info->blocks_per_sm = per_sm;
+        info->launches = 1;
+        info->rays_per_lane = 1;
+        info->sweep = kSweepPacked;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+MagicDiv make_magic_div(uint32_t d) {
+    // Granlund & Montgomery, "Division by invariant integers using multiplication", fig. 4.1 (N = 32)
+    MagicDiv k;
+    uint32_t L = 0;
+    while ((1ull << L) < (unsigned long long)d) ++L;
+    k.m = (uint32_t)(((1ull << 32) * ((1ull << L) - (unsigned long long)d)) / (unsigned long long)d + 1ull);
+    k.sh1 = L < 1u ? L : 1u;
+    k.sh2 = L > 0u ? L - 1u : 0u;
+    return k;
+}
+
+cudaError_t launch_uv_tables(int W, int H, float* u_tab, float* v_tab, cudaStream_t stream) {
+    const int n = W > H ? W : H;
+    if (n <= 0) return cudaSuccess;
+    uv_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(W, H, u_tab, v_tab);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fused_trace2(const TraceParams& p, int num_sms, int blocks_per_sm_override, int coop,
+                                cudaStream_t stream, LaunchInfo* info) {
+    const bool multi = p.n_spheres > kTileSpheres;
+    if (coop == 4) {
+        return multi ? launch_variant2<true, 4>(p, num_sms, blocks_per_sm_override, stream, info)
+                     : launch_variant2<false, 4>(p, num_sms, blocks_per_sm_override, stream, info);
+    }
+    return multi ? launch_variant2<true, 2>(p, num_sms, blocks_per_sm_override, stream, info)
+                 : launch_variant2<false, 2>(p, num_sms, blocks_per_sm_override, stream, info);
+}
+
+}  // namespace rtw

@@ -13,10 +13,22 @@ namespace rtw {
 //   kind   : n x u32
 //   accum  : n_rows*W x 4 x i64  fixed-point radiance sums (r,g,b,pad), scale 2^fx_bits, order-independent atomics
 //   counters[0] = path ticket counter, counters[1] = ray segments traced
+// unsigned division by an invariant through multiply + shifts (make_magic_div); exact for every 32-bit dividend
+struct MagicDiv {
+    uint32_t m, sh1, sh2;
+};
+
 struct TraceParams {
     DevCamera cam;
     const float4* geom;
     const float4* geom_pairs;  // pair layout for the packed sweep: {xa,xb,ya,yb}{za,zb,ra,rb} per 2 spheres
+    // RTW_TAIL_UNIFIED only: AoS copy of the list in the order the lanes of a cooperating group meet the spheres
+    // (entry (c*coop + h)*32 + j = list index c*32*coop + 2*((j>>1)*coop + h) + (j&1)), zero padded to whole
+    // super-chunks of 32*coop spheres; matches the `coop` the kernel is launched with
+    const float4* geom_perm;
+    const float* u_tab;  // W entries: T((col+1)/W), src/render.jl:26
+    const float* v_tab;  // H entries: T((H-1-i0)/H), src/render.jl:27
+    MagicDiv div_spp, div_w;
     const float4* mat;
     const uint32_t* kind;
     uint32_t n_spheres;
@@ -59,6 +71,12 @@ constexpr uint32_t kTileSpheres = 1024;
 
 cudaError_t launch_fused_trace(const TraceParams& p, int num_sms, int blocks_per_sm_override, int rays_per_lane,
                                int sweep, int coop, cudaStream_t stream, LaunchInfo* info);
+// RTW_TAIL_UNIFIED (rtw_fused2.cu): packed sweep, one path per lane, coop = 2 or 4; needs geom_perm / u_tab / v_tab /
+// div_* of TraceParams
+cudaError_t launch_fused_trace2(const TraceParams& p, int num_sms, int blocks_per_sm_override, int coop,
+                                cudaStream_t stream, LaunchInfo* info);
+cudaError_t launch_uv_tables(int W, int H, float* u_tab, float* v_tab, cudaStream_t stream);
+MagicDiv make_magic_div(uint32_t d);
 // RTW_MODE_WAVEFRONT (rtw_wavefront.cu); synchronises `stream` internally (host-driven step loop)
 size_t wavefront_bytes(uint32_t capacity);
 cudaError_t launch_wavefront_trace(const TraceParams& p, const WavefrontBuffers& b, int num_sms, unsigned int* h_traced,

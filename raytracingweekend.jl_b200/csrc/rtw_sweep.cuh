@@ -189,18 +189,20 @@ __device__ __forceinline__ void sweep_masks_packed(const float4* __restrict__ ti
 #pragma unroll
         for (int r = 0; r < NS; ++r) m[r] = 0u;
         const uint32_t pairs_here = npairs - c * kSuperPairs;  // pairs left from this super-chunk on
-        if (pairs_here >= kSuperPairs) {
+        if (pairs_here > kSuperPairs || (pairs_here == kSuperPairs && (count & 1u) == 0u)) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) test_pair_packed<NS>(ch[2 * kCoop * i], ch[2 * kCoop * i + 1], o, d, m);
         } else {
-            // ragged last super-chunk: only the pairs that exist (no padded arithmetic); left-align the mask and
-            // mark the missing tests as misses
+            // last super-chunk, ragged or ending in the zero pad partner of an odd last sphere: only the pairs that
+            // exist (no padded arithmetic); left-align the mask and mark the missing tests as misses
             const uint32_t mine = pairs_here > coop_h ? (pairs_here - coop_h + kCoop - 1u) / kCoop : 0u;
 #pragma unroll 1
             for (uint32_t i = 0; i < mine; ++i) test_pair_packed<NS>(ch[2 * kCoop * i], ch[2 * kCoop * i + 1], o, d, m);
-            const uint32_t sh = 32u - 2u * mine;  // 2..32
+            const uint32_t sh = 32u - 2u * mine;  // 0..32
+            // the pad partner is the second half of the last pair: the last test of the lane that holds that pair
+            const uint32_t pad = ((count & 1u) != 0u && coop_h == (pairs_here - 1u) % kCoop) ? (1u << sh) : 0u;
 #pragma unroll
-            for (int r = 0; r < NS; ++r) m[r] = sh >= 32u ? 0xffffffffu : ((m[r] << sh) | ((1u << sh) - 1u));
+            for (int r = 0; r < NS; ++r) m[r] = sh >= 32u ? 0xffffffffu : ((m[r] << sh) | ((1u << sh) - 1u) | pad);
         }
 #pragma unroll
         for (int r = 0; r < NS; ++r) {

@@ -25,15 +25,17 @@ def _compare(img_gpu, img_cpu, max_mismatch_frac=1e-3):
     return linf, n_diff
 
 
-@pytest.mark.parametrize("rays,sweep,coop", [(1, 1, 1), (2, 1, 1), (1, 2, 1), (2, 2, 1), (4, 2, 1), (1, 3, 1), (2, 3, 1),
-                                             (4, 3, 1), (1, 3, 2), (1, 3, 4)])
-def test_cfg1_scene_2_spheres_all_variants(rtw, oracle, renderer, scenes, rays, sweep, coop):
+@pytest.mark.parametrize("rays,sweep,coop,tail", [(1, 1, 1, 1), (2, 1, 1, 1), (1, 2, 1, 1), (2, 2, 1, 1), (4, 2, 1, 1),
+                                                  (1, 3, 1, 1), (2, 3, 1, 1), (4, 3, 1, 1), (1, 3, 2, 1), (1, 3, 4, 1),
+                                                  (1, 3, 2, 2), (1, 3, 4, 2)])
+def test_cfg1_scene_2_spheres_all_variants(rtw, oracle, renderer, scenes, rays, sweep, coop, tail):
     # BASELINE configs[0]: scene_2_spheres, 96x54, 16 spp, 4 bounces, Float32 (test/runtests.jl:194 shape)
     g, m, k = scenes["two"]
     cam = rtw.t_default_cam()
     renderer.set_option(rtw.RTW_OPT_RAYS_PER_LANE, rays)
     renderer.set_option(rtw.RTW_OPT_SWEEP, sweep)
     renderer.set_option(rtw.RTW_OPT_COOP, coop)
+    renderer.set_option(rtw.RTW_OPT_TAIL, tail)
     try:
         renderer.set_scene((g, m, k))
         img = renderer.render(cam, 96, 16, max_depth=4, seed=1)
@@ -42,6 +44,7 @@ def test_cfg1_scene_2_spheres_all_variants(rtw, oracle, renderer, scenes, rays, 
         renderer.set_option(rtw.RTW_OPT_RAYS_PER_LANE, 0)
         renderer.set_option(rtw.RTW_OPT_SWEEP, 0)
         renderer.set_option(rtw.RTW_OPT_COOP, 0)
+        renderer.set_option(rtw.RTW_OPT_TAIL, 0)
     ref, _, ost = oracle.render(g, m, k, cam.as_array(), 96, 16, max_depth=4, seed=1, n_threads=1)
     _compare(img, ref)
     assert st["paths"] == ost["paths"] == 96 * 54 * 16
@@ -49,18 +52,21 @@ def test_cfg1_scene_2_spheres_all_variants(rtw, oracle, renderer, scenes, rays, 
     assert st["sphere_tests"] == ost["sphere_tests"]
 
 
-@pytest.mark.parametrize("coop", [1, 2, 4])
-def test_random_spheres_coop_variants_identical(rtw, oracle, renderer, scenes, coop):
+@pytest.mark.parametrize("coop,tail", [(1, 1), (2, 1), (4, 1), (2, 2), (4, 2)])
+def test_random_spheres_coop_variants_identical(rtw, oracle, renderer, scenes, coop, tail):
     # the lane-cooperative sweep merges per-lane partial closest hits: same image bits as the oracle on the
-    # 484-sphere scene (odd super-chunk tails, ties, inside hits)
+    # 484-sphere scene (odd super-chunk tails, ties, inside hits); tail 1 = per-state shading/regeneration,
+    # tail 2 = unified Philox block + cooperative rejection sampling (rtw_fused2.cu)
     g, m, k = scenes["random"]
     cam = rtw.t_cam1()
     renderer.set_option(rtw.RTW_OPT_COOP, coop)
+    renderer.set_option(rtw.RTW_OPT_TAIL, tail)
     try:
         img = renderer.render(cam, 200, 16, max_depth=16, seed=3, scene=(g, m, k))
         st = dict(renderer.last_stats)
     finally:
         renderer.set_option(rtw.RTW_OPT_COOP, 0)
+        renderer.set_option(rtw.RTW_OPT_TAIL, 0)
     ref, _, ost = oracle.render(g, m, k, cam.as_array(), 200, 16, max_depth=16, seed=3)
     _compare(img, ref)
     assert st["ray_segments"] == ost["ray_segments"]
@@ -90,6 +96,24 @@ def test_other_reference_scenes(rtw, oracle, renderer, scenes, name, cam_name, d
     ref, _, ost = oracle.render(g, m, k, cam.as_array(), 160, 32, max_depth=depth, seed=7)
     _compare(img, ref)
     assert renderer.last_stats["ray_segments"] == ost["ray_segments"]
+
+
+@pytest.mark.parametrize("tail", [1, 2])
+def test_tail_variants_on_reference_scenes_and_odd_shapes(rtw, oracle, renderer, scenes, tail):
+    # both tails of the fused kernel on: the dielectric scenes (coin flips, total internal reflection, hollow bubble),
+    # the depth-of-field camera (disk rejection), 1 spp (un-jittered sample only; division by 1), odd widths
+    # (multiply-shift division by W), deep paths and a 3-row tile split
+    renderer.set_option(rtw.RTW_OPT_TAIL, tail)
+    try:
+        for name, cam, W, spp, depth, seed in [("diel", rtw.t_cam2(), 160, 32, 16, 7), ("bubble", rtw.t_default_cam(), 131, 9, 50, 2),
+                                               ("four", rtw.t_default_cam(), 77, 1, 16, 3), ("random", rtw.t_cam1(), 97, 5, 50, 4),
+                                               ("bluered", rtw.t_cam2(), 33, 1000, 6, 5)]:
+            img = renderer.render(cam, W, spp, max_depth=depth, seed=seed, scene=scenes[name])
+            ref, _, ost = oracle.render(*scenes[name], cam.as_array(), W, spp, max_depth=depth, seed=seed)
+            _compare(img, ref)
+            assert renderer.last_stats["ray_segments"] == ost["ray_segments"], (name, tail)
+    finally:
+        renderer.set_option(rtw.RTW_OPT_TAIL, 0)
 
 
 def test_golden_fixture_cfg1(rtw, renderer, scenes):
@@ -146,16 +170,19 @@ def test_large_list_streams_through_tma_tiles(rtw, oracle, renderer):
     scene = rtw.flatten_scene(rtw.scene_random_spheres(half_extent=26))  # ~2700 spheres, ragged last tile
     assert len(scene[2]) > 2 * 1024 and len(scene[2]) % 1024 != 0
     cam = rtw.t_cam1()
-    for rays, sweep, coop in [(1, 3, 2), (1, 3, 4), (1, 3, 1), (2, 3, 1), (2, 2, 1), (1, 1, 1)]:
+    for rays, sweep, coop, tail in [(1, 3, 2, 2), (1, 3, 4, 2), (1, 3, 2, 1), (1, 3, 4, 1), (1, 3, 1, 1), (2, 3, 1, 1), (2, 2, 1, 1),
+                                    (1, 1, 1, 1)]:
         renderer.set_option(rtw.RTW_OPT_RAYS_PER_LANE, rays)
         renderer.set_option(rtw.RTW_OPT_SWEEP, sweep)
         renderer.set_option(rtw.RTW_OPT_COOP, coop)
+        renderer.set_option(rtw.RTW_OPT_TAIL, tail)
         try:
             img = renderer.render(cam, 128, 8, max_depth=16, scene=scene)
         finally:
             renderer.set_option(rtw.RTW_OPT_RAYS_PER_LANE, 0)
             renderer.set_option(rtw.RTW_OPT_SWEEP, 0)
             renderer.set_option(rtw.RTW_OPT_COOP, 0)
+            renderer.set_option(rtw.RTW_OPT_TAIL, 0)
         ref, _, ost = oracle.render(*scene, cam.as_array(), 128, 8, max_depth=16)
         _compare(img, ref)
         assert renderer.last_stats["ray_segments"] == ost["ray_segments"]
@@ -297,22 +324,25 @@ def test_ragged_list_sizes_all_sweeps(rtw, oracle, renderer, n):
     sub = (g[order].copy(), m[order].copy(), k[order].copy())
     cam = rtw.t_cam1()
     ref, _, ost = oracle.render(*sub, cam.as_array(), 64, 4, max_depth=12, seed=11)
-    variants = [(1, 3, 1, 0), (1, 3, 2, 0), (1, 3, 4, 0), (2, 3, 1, 0), (1, 2, 1, 0)]
+    S, U = rtw.RTW_TAIL_SPLIT, rtw.RTW_TAIL_UNIFIED
+    variants = [(1, 3, 1, 0, S), (1, 3, 2, 0, S), (1, 3, 4, 0, S), (1, 3, 2, 0, U), (1, 3, 4, 0, U), (2, 3, 1, 0, S),
+                (1, 2, 1, 0, S)]
     if n <= 1024:
-        variants += [(1, 3, 2, 1), (1, 3, 2, 2)]  # split wavefront and CTA wavefront keep the list in one tile
-    for rays, sweep, coop, mode in variants:
+        variants += [(1, 3, 2, 1, S), (1, 3, 2, 2, S)]  # split wavefront and CTA wavefront keep the list in one tile
+    for rays, sweep, coop, mode, tail in variants:
         renderer.set_option(rtw.RTW_OPT_RAYS_PER_LANE, rays)
         renderer.set_option(rtw.RTW_OPT_SWEEP, sweep)
         renderer.set_option(rtw.RTW_OPT_COOP, coop)
         renderer.set_option(rtw.RTW_OPT_MODE, mode)
+        renderer.set_option(rtw.RTW_OPT_TAIL, tail)
         try:
             img = renderer.render(cam, 64, 4, max_depth=12, seed=11, scene=sub)
             segs = renderer.last_stats["ray_segments"]
         finally:
-            for opt in (rtw.RTW_OPT_RAYS_PER_LANE, rtw.RTW_OPT_SWEEP, rtw.RTW_OPT_COOP, rtw.RTW_OPT_MODE):
+            for opt in (rtw.RTW_OPT_RAYS_PER_LANE, rtw.RTW_OPT_SWEEP, rtw.RTW_OPT_COOP, rtw.RTW_OPT_MODE, rtw.RTW_OPT_TAIL):
                 renderer.set_option(opt, 0)
         _compare(img, ref)
-        assert segs == ost["ray_segments"], (n, rays, sweep, coop, mode)
+        assert segs == ost["ray_segments"], (n, rays, sweep, coop, mode, tail)
 
 
 def test_high_seed_bits_and_many_samples(rtw, oracle, renderer, scenes):

@@ -208,6 +208,7 @@ int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, in
         p.geom_perm = nullptr;
         p.u_tab = p.v_tab = nullptr;
         p.div_spp = p.div_w = rtw::MagicDiv{0u, 0u, 0u};
+        std::memset(p.rk, 0, sizeof p.rk);
         p.mat = ds.d_mat;
         p.kind = ds.d_kind;
         p.n_spheres = ctx->n_spheres;
@@ -244,6 +245,10 @@ int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, in
                 p.v_tab = ds.d_uv + W;
                 p.div_spp = rtw::make_magic_div((uint32_t)spp);
                 p.div_w = rtw::make_magic_div((uint32_t)W);
+                for (uint32_t r = 0; r < 10u; ++r) {
+                    p.rk[2 * r] = p.key0 + r * rtw::kPhiloxW0;
+                    p.rk[2 * r + 1] = p.key1 + r * rtw::kPhiloxW1;
+                }
                 RTW_CUDA(ctx, rtw::launch_fused_trace2(p, ds.num_sms, ctx->blocks_per_sm, coop, stream, &li));
             } else {
                 RTW_CUDA(ctx, rtw::launch_fused_trace(p, ds.num_sms, ctx->blocks_per_sm, rays, sweep, coop, stream, &li));

@@ -37,6 +37,40 @@ __device__ __forceinline__ uint32_t bfind_u32(uint32_t x) {  // position of the 
     return r;
 }
 
+// ((1 << width) - 1), all ones for width >= 32
+__device__ __forceinline__ uint32_t low_mask(uint32_t width) {
+    uint32_t r;
+    asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(r) : "r"(0u), "r"(width));
+    return r;
+}
+
+// Philox4x32-10 with the ten round keys read from the kernel parameter block (constant bank operands) instead of
+// being re-derived (k += W per round) by every evaluation; same function as philox_block (rtw_device.cuh)
+__device__ __forceinline__ u32x4 philox_block_rk(const TraceParams& P, uint32_t sample, uint32_t pixel, uint32_t event,
+                                                 uint32_t block) {
+    uint32_t c0 = block, c1 = sample, c2 = pixel, c3 = event;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
+        const uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ P.rk[2 * r];
+        const uint32_t n2 = hi0 ^ c3 ^ P.rk[2 * r + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    return u32x4{c0, c1, c2, c3};
+}
+
+// cooperative rejection sampling: with `cnt` lanes in need, each gets per = 32 / cnt helper lanes;
+// entry = per | (ceil(256 / per) << 8), so that lane / per = (lane * (entry >> 8)) >> 8 for lane < 32
+__constant__ uint32_t c_coop_tab[33] = {
+    0u,
+    32u | (8u << 8), 16u | (16u << 8), 10u | (26u << 8), 8u | (32u << 8), 6u | (43u << 8), 5u | (52u << 8),
+    4u | (64u << 8), 4u | (64u << 8), 3u | (86u << 8), 3u | (86u << 8), 2u | (128u << 8), 2u | (128u << 8),
+    2u | (128u << 8), 2u | (128u << 8), 2u | (128u << 8), 2u | (128u << 8), 1u | (256u << 8), 1u | (256u << 8),
+    1u | (256u << 8), 1u | (256u << 8), 1u | (256u << 8), 1u | (256u << 8), 1u | (256u << 8), 1u | (256u << 8),
+    1u | (256u << 8), 1u | (256u << 8), 1u | (256u << 8), 1u | (256u << 8), 1u | (256u << 8), 1u | (256u << 8),
+    1u | (256u << 8), 1u | (256u << 8)};
+
 // random_between(-1, 1) of the word's uniform (src/rand.jl:24): 2*(k*2^-23) - 1 = k*2^-22 - 1, exact either way
 __device__ __forceinline__ float pm1x(uint32_t w) { return fmaf((float)(w >> 9), 2.384185791015625e-07f, -1.0f); }
 
@@ -48,6 +82,9 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {  // 32-bit shared-wind
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
@@ -84,7 +121,7 @@ __device__ __forceinline__ void walk_candidates_perm(const float4* __restrict__ 
                 code31 = (c * kCoop + coop_h) * 32u + 31u;
             }
             const uint32_t p = bfind_u32(cand);
-            cand &= (1u << p) - 1u;  // p is the highest set bit
+            cand &= low_mask(p);  // p is the highest set bit
             const float4 s = lds128(a31 - 16u * p);
             // scalar redo of src/hit.jl:13-18: bit-identical to the packed values of the sweep
             const float ocx = ox - s.x, ocy = oy - s.y, ocz = oz - s.z;
@@ -109,6 +146,62 @@ __device__ __forceinline__ void walk_candidates_perm(const float4* __restrict__ 
             best_k[r] = (int)(c * (32u * kCoop) + 2u * ((j >> 1) * kCoop + coop_h) + (j & 1u));
         } else {
             best_k[r] = -1;
+        }
+    }
+}
+
+// The branch-free part of the packed sweep (same tests, same mask words as sweep_masks_packed in rtw_sweep.cuh),
+// addressed through 32-bit shared-window pointers that advance per super-chunk: `tile_lane` = address of this
+// lane's first pair of super-chunk 0, `mask_lane` = address of this lane's mask word 0.
+template <int NS, int kCoop, int kBlock>
+__device__ __forceinline__ void sweep_masks_packed2(uint32_t tile_lane, uint32_t count, uint32_t coop_h,
+                                                    uint32_t mask_lane, const f3 (&o)[NS], const f3 (&d)[NS],
+                                                    uint32_t (&summary)[NS]) {
+    constexpr uint32_t kSuper = 32u * kCoop;  // spheres per super-chunk = float4 entries of pair layout
+    constexpr uint32_t kSuperPairs = 16u * kCoop;
+    const uint32_t npairs = (count + 1u) >> 1;
+    // super-chunks that are complete and do not end in the zero pad partner of an odd last sphere
+    const uint32_t nfull = (count & 1u) ? (npairs - 1u) / kSuperPairs : npairs / kSuperPairs;
+#pragma unroll
+    for (int r = 0; r < NS; ++r) summary[r] = 0u;
+    uint32_t a = tile_lane, ma = mask_lane, bit = 1u;
+    for (uint32_t c = 0; c < nfull; ++c) {
+        uint32_t m[NS];
+#pragma unroll
+        for (int r = 0; r < NS; ++r) m[r] = 0u;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            test_pair_packed<NS>(lds128(a + (uint32_t)i * (kCoop * 32u)), lds128(a + (uint32_t)i * (kCoop * 32u) + 16u), o, d, m);
+#pragma unroll
+        for (int r = 0; r < NS; ++r) {
+            sts32(ma + (uint32_t)r * (kBlock * 4u), m[r]);
+            summary[r] |= m[r] != 0xffffffffu ? bit : 0u;
+        }
+        a += kSuper * 16u;
+        ma += NS * kBlock * 4u;
+        bit <<= 1;
+    }
+    const uint32_t pairs_here = npairs - nfull * kSuperPairs;  // 0 .. kSuperPairs
+    if (pairs_here != 0u) {
+        // last super-chunk, ragged or ending in the pad: only the pairs that exist (no padded arithmetic);
+        // left-align the mask and mark the missing tests (and the pad) as misses
+        uint32_t m[NS];
+#pragma unroll
+        for (int r = 0; r < NS; ++r) m[r] = 0u;
+        const uint32_t mine = pairs_here > coop_h ? (pairs_here - coop_h + kCoop - 1u) / kCoop : 0u;
+#pragma unroll 1
+        for (uint32_t i = 0; i < mine; ++i) {
+            test_pair_packed<NS>(lds128(a), lds128(a + 16u), o, d, m);
+            a += kCoop * 32u;
+        }
+        const uint32_t sh = 32u - 2u * mine;  // 0..32
+        const uint32_t pad = ((count & 1u) != 0u && coop_h == (pairs_here - 1u) % kCoop) ? (1u << sh) : 0u;
+        const uint32_t fill = low_mask(sh) | pad;
+#pragma unroll
+        for (int r = 0; r < NS; ++r) {
+            m[r] = sh >= 32u ? 0xffffffffu : ((m[r] << sh) | fill);
+            sts32(ma + (uint32_t)r * (kBlock * 4u), m[r]);
+            summary[r] |= m[r] != 0xffffffffu ? bit : 0u;
         }
     }
 }
@@ -138,7 +231,7 @@ __device__ __forceinline__ void closest_hit_single_tile(const float4* __restrict
             sa[q] = __shfl_xor_sync(kFullMask, alive ? 1 : 0, q) != 0;
         }
     }
-    sweep_masks_packed<kCoop, kCoop, kBlock>(tile, count, h, s_mask, so, sd, summary);
+    sweep_masks_packed2<kCoop, kCoop, kBlock>(smem_u32(tile) + h * 32u, count, h, smem_u32(s_mask), so, sd, summary);
     walk_candidates_perm<kCoop, kCoop, kBlock>(aos_perm, h, s_mask, so, sd, sa, summary, bt, bk);
     best_t = bt[0];
     best_k = bk[0];
@@ -189,7 +282,6 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const uint32_t k0 = P.key0, k1 = P.key1;
     uint4* const coop_slot = s_coop[threadIdx.x >> 5];
 
     // path state of the lane
@@ -282,7 +374,7 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
         // ------------------------------------------------------------ block 0 of the event, for every lane at once
         // continuing lanes: event = index of this hit (scatter draws); new lanes: event 0 (primary-ray draws)
         const uint32_t ev = cont ? nhits : 0u;
-        const u32x4 b0 = philox_block(PathRng{sample, pixel}, ev, 0u, k0, k1);
+        const u32x4 b0 = philox_block_rk(P, sample, pixel, ev, 0u);
         float px = pm1x(b0.w0), py = pm1x(b0.w1), pz = pm1x(b0.w2);
         const float pw = pm1x(b0.w3);
         const bool ball = cont && kind != 2u;  // Lambertian and Metal draw a unit vector (Metal even when fuzz == 0)
@@ -313,31 +405,34 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
             uint32_t blk = 1u;  // next unevaluated block; uniform: every needy lane has failed the same attempts
             while (needm) {
                 const uint32_t cnt = (uint32_t)__popc(needm);
-                const uint32_t sh = cnt <= 1u ? 5u : (uint32_t)__clz((int)(cnt - 1u)) - 27u;  // 2^sh helpers per lane
+                const uint32_t tab = c_coop_tab[cnt];
+                const uint32_t per = tab & 0xffu;  // helper lanes (= attempts evaluated) per needy lane: 32 / cnt
                 const uint32_t rank = (uint32_t)__popc(needm & lt_mask);
                 if (need) coop_slot[rank] = make_uint4(sample, pixel, ev | (newp ? 0x80000000u : 0u), 0u);
                 __syncwarp();
-                const uint32_t hq = lane >> sh, ha = lane & ((1u << sh) - 1u);
+                const uint32_t hq = (lane * (tab >> 8)) >> 8;  // lane / per: the request this lane helps
+                const uint32_t ha = lane - hq * per;           // and which of its attempts
                 const uint4 tsk = coop_slot[hq < cnt ? hq : 0u];
-                const u32x4 hb = philox_block(PathRng{tsk.x, tsk.y}, tsk.z & 0x7fffffffu, blk + ha, k0, k1);
+                const u32x4 hb = philox_block_rk(P, tsk.x, tsk.y, tsk.z & 0x7fffffffu, blk + ha);
                 float hx = pm1x(hb.w0), hy = pm1x(hb.w1);
                 const float hz = pm1x(hb.w2), hw = pm1x(hb.w3);
                 const float q01 = fmaf(hy, hy, hx * hx);
                 const float qball = fmaf(hz, hz, q01);
                 const float q23 = fmaf(hw, hw, hz * hz);
-                const bool is_disk = (tsk.z >> 31) != 0u;
+                const bool is_disk = (int)tsk.z < 0;
                 const bool ok01 = q01 <= 1.0f;
-                const bool ok = hq < cnt && (is_disk ? (ok01 || q23 <= 1.0f) : (qball <= 1.0f));
-                if (is_disk && !ok01) { hx = hz; hy = hw; }
+                const float qsel = is_disk ? fminf(q01, q23) : qball;
+                const bool ok = (hq < cnt) & (qsel <= 1.0f);
+                if (is_disk & !ok01) { hx = hz; hy = hw; }
                 const unsigned okm = __ballot_sync(kFullMask, ok);
-                const uint32_t wmask = sh >= 5u ? 0xffffffffu : ((1u << (1u << sh)) - 1u);
-                const uint32_t mine = need ? ((okm >> (rank << sh)) & wmask) : 0u;
-                const uint32_t src = mine ? (rank << sh) + (uint32_t)__ffs((int)mine) - 1u : lane;
+                const uint32_t first = rank * per;
+                const uint32_t mine = need ? ((okm >> first) & low_mask(per)) : 0u;
+                const uint32_t src = mine ? first + (uint32_t)__ffs((int)mine) - 1u : lane;
                 const float gx = __shfl_sync(kFullMask, hx, src);
                 const float gy = __shfl_sync(kFullMask, hy, src);
                 const float gz = __shfl_sync(kFullMask, hz, src);
                 if (mine) { px = gx; py = gy; pz = gz; need = false; }
-                blk += 1u << sh;
+                blk += per;
                 needm = __ballot_sync(kFullMask, need);
             }
         }

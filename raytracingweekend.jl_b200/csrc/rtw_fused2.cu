@@ -206,37 +206,87 @@ __device__ __forceinline__ void sweep_masks_packed2(uint32_t tile_lane, uint32_t
     }
 }
 
-// closest hit of one ray per lane over a single resident tile: ray exchange inside the lane group, packed mask
-// sweep, candidate walk over the permuted copy, merge of the partial results (list-order tie rule)
-template <int kCoop, int kBlock>
-__device__ __forceinline__ void closest_hit_single_tile(const float4* __restrict__ tile,
-                                                        const float4* __restrict__ aos_perm, uint32_t count,
-                                                        uint32_t* __restrict__ s_mask, const f3 o, const f3 d,
-                                                        const bool alive, float& best_t, int& best_k) {
-    const uint32_t h = threadIdx.x & (kCoop - 1);
-    f3 so[kCoop], sd[kCoop];
-    bool sa[kCoop];
-    float bt[kCoop];
-    int bk[kCoop];
-    uint32_t summary[kCoop];
+// Candidate resolution straight from a pair-layout tile (streamed lists: no lane-order copy in shared memory).
+// `tile_lane` = address of this lane's first pair of super-chunk 0, k_base = list index of the tile's first sphere;
+// best_t / best_k carry the closest hit over the tiles walked so far (tiles come in list order, so ties still go to
+// the later sphere).
+__device__ __forceinline__ float lds32f(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+template <int NS, int kCoop, int kBlock>
+__device__ __forceinline__ void walk_candidates_pairs(uint32_t tile_lane, uint32_t coop_h, uint32_t mask_lane,
+                                                      uint32_t k_base, const f3 (&o)[NS], const f3 (&d)[NS],
+                                                      const bool (&alive)[NS], const uint32_t (&summary)[NS],
+                                                      float (&best_t)[NS], int (&best_k)[NS]) {
+    const float tmin = 1e-4f;
 #pragma unroll
-    for (int q = 0; q < kCoop; ++q) {  // slot q holds the ray of lane (lane ^ q)
-        if (q == 0) {
-            so[0] = o; sd[0] = d; sa[0] = alive;
-        } else {
-            so[q] = mk3(__shfl_xor_sync(kFullMask, o.x, q), __shfl_xor_sync(kFullMask, o.y, q),
-                        __shfl_xor_sync(kFullMask, o.z, q));
-            sd[q] = mk3(__shfl_xor_sync(kFullMask, d.x, q), __shfl_xor_sync(kFullMask, d.y, q),
-                        __shfl_xor_sync(kFullMask, d.z, q));
-            sa[q] = __shfl_xor_sync(kFullMask, alive ? 1 : 0, q) != 0;
+    for (int r = 0; r < NS; ++r) {
+        uint32_t sum = alive[r] ? summary[r] : 0u;
+        uint32_t cand = 0u, pbase = 0u, klbase = 0u;
+        float bt = best_t[r];
+        int bk = best_k[r];
+        const float ox = o[r].x, oy = o[r].y, oz = o[r].z, dx = d[r].x, dy = d[r].y, dz = d[r].z;
+        for (;;) {
+            if (cand == 0u) {
+                if (sum == 0u) break;
+                const uint32_t c = (uint32_t)__ffs((int)sum) - 1u;
+                sum &= sum - 1u;
+                cand = ~lds32(mask_lane + (c * NS + r) * (kBlock * 4u));
+                pbase = tile_lane + c * (kCoop * 32u * 16u);
+                klbase = k_base + c * (32u * kCoop) + 2u * coop_h;
+            }
+            const uint32_t p = bfind_u32(cand);
+            cand &= low_mask(p);
+            const uint32_t j = 31u - p;  // this lane's j-th test of the super-chunk: pair j>>1, half j&1
+            const uint32_t addr = pbase + (j >> 1) * (kCoop * 32u) + (j & 1u) * 4u;
+            const float sx = lds32f(addr), sy = lds32f(addr + 8u), sz = lds32f(addr + 16u), sr = lds32f(addr + 24u);
+            const float ocx = ox - sx, ocy = oy - sy, ocz = oz - sz;
+            const float hb = fmaf(ocz, dz, fmaf(ocy, dy, ocx * dx));
+            const float cq = fmaf(-sr, sr, fmaf(ocz, ocz, fmaf(ocy, ocy, ocx * ocx)));
+            if (hb > 0.0f && cq > 0.0f) continue;  // wholly behind the origin: both roots < tmin
+            const float sq = __fsqrt_rn(fmaf(hb, hb, -cq));
+            const float r1 = -hb - sq, r2 = -hb + sq;
+            const bool bad1 = r1 < tmin || bt < r1;
+            const bool bad2 = r2 < tmin || bt < r2;
+            if (!(bad1 && bad2)) {
+                bt = bad1 ? r2 : r1;
+                bk = (int)(klbase + (j >> 1) * (2u * kCoop) + (j & 1u));
+            }
         }
+        best_t[r] = bt;
+        best_k[r] = bk;
     }
-    sweep_masks_packed2<kCoop, kCoop, kBlock>(smem_u32(tile) + h * 32u, count, h, smem_u32(s_mask), so, sd, summary);
-    walk_candidates_perm<kCoop, kCoop, kBlock>(aos_perm, h, s_mask, so, sd, sa, summary, bt, bk);
+}
+
+// slot q of a lane holds the ray of lane (lane ^ q) of its cooperating group
+template <int kCoop>
+__device__ __forceinline__ void exchange_rays(const f3 o, const f3 d, const bool alive, f3 (&so)[kCoop],
+                                              f3 (&sd)[kCoop], bool (&sa)[kCoop]) {
+    so[0] = o;
+    sd[0] = d;
+    sa[0] = alive;
+#pragma unroll
+    for (int q = 1; q < kCoop; ++q) {
+        so[q] = mk3(__shfl_xor_sync(kFullMask, o.x, q), __shfl_xor_sync(kFullMask, o.y, q),
+                    __shfl_xor_sync(kFullMask, o.z, q));
+        sd[q] = mk3(__shfl_xor_sync(kFullMask, d.x, q), __shfl_xor_sync(kFullMask, d.y, q),
+                    __shfl_xor_sync(kFullMask, d.z, q));
+        sa[q] = __shfl_xor_sync(kFullMask, alive ? 1 : 0, q) != 0;
+    }
+}
+
+// lane ^ q holds, in ITS slot q, the partial closest hit for my ray: merge with the list-order tie rule
+// (equal t => later sphere, src/hit.jl:24-26,44-46)
+template <int kCoop>
+__device__ __forceinline__ void merge_partial_hits(const float (&bt)[kCoop], const int (&bk)[kCoop], float& best_t,
+                                                   int& best_k) {
     best_t = bt[0];
     best_k = bk[0];
 #pragma unroll
-    for (int q = 1; q < kCoop; ++q) {  // lane ^ q holds, in ITS slot q, the partial result for my ray
+    for (int q = 1; q < kCoop; ++q) {
         const float pt = __shfl_xor_sync(kFullMask, bt[q], q);
         const int pk = __shfl_xor_sync(kFullMask, bk[q], q);
         if (pk >= 0 && (best_k < 0 || pt < best_t || (pt == best_t && pk > best_k))) {
@@ -301,8 +351,12 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
         if (alive) {
             seg_count += 1;
             if (best_k < 0) {  // miss: sky (src/ray_color.jl:36), path ends
-                double sr, sg, sb;
-                skycolor(d, sr, sg, sb);
+                // skycolor, src/ray_color.jl:1-6: (1-t)*white + t*skyblue with Float64 literals; x*1.0 is exact and omitted
+                const float t = 0.5f * (d.y + 1.0f);
+                const double a1 = (double)(1.0f - t), w1 = (double)t;
+                const double sr = __dadd_rn(a1, __dmul_rn(w1, 0.5));
+                const double sg = __dadd_rn(a1, __dmul_rn(w1, 0.7));
+                const double sb = __dadd_rn(a1, w1);
                 // accumulate (src/render.jl:38): order-independent fixed-point atomics
                 unsigned long long* a = P.accum + (unsigned long long)pix_local * 4ull;
                 atomicAdd(a + 0, (unsigned long long)__double2ll_rn(__dmul_rn(thr_r, sr) * P.fx_scale));
@@ -507,36 +561,49 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
         // ------------------------------------------------------------ intersect: closest hit over the list
         best_t = __int_as_float(0x7f800000);  // typemax(T) = Inf, src/ray_color.jl:19
         best_k = -1;
-        if (!kMulti) {
-            closest_hit_single_tile<kCoop, kTraceBlock>(s_tile0, s_tile1, n, s_mask, o, d, alive, best_t, best_k);
-        } else {
-            f3 oa[1] = {o}, da[1] = {d};
-            bool aa[1] = {alive};
-            float bta[1] = {best_t};
-            int bka[1] = {best_k};
-            if (threadIdx.x == 0) {  // prologue: tile 0 -> buffer 0
-                const uint32_t cnt = n_stage < kTileSpheres ? n_stage : kTileSpheres;
-                mbar_arrive_expect_tx(&s_bar[0], cnt * 16u);
-                tma_bulk_g2s(s_tile0, g_src, cnt * 16u, &s_bar[0]);
-            }
-            for (uint32_t t = 0; t < n_tiles; ++t) {
-                const uint32_t base = t * kTileSpheres;
-                const uint32_t cnt = n - base < kTileSpheres ? n - base : kTileSpheres;
-                if (threadIdx.x == 0 && t + 1u < n_tiles) {  // prefetch tile t+1 into the other buffer
-                    const uint32_t nb = base + kTileSpheres;
-                    const uint32_t ncnt = n_stage - nb < kTileSpheres ? n_stage - nb : kTileSpheres;
-                    unsigned long long* bar = &s_bar[(t + 1u) & 1u];
-                    mbar_arrive_expect_tx(bar, ncnt * 16u);
-                    tma_bulk_g2s((t & 1u) ? s_tile0 : s_tile1, g_src + nb, ncnt * 16u, bar);
+        {
+            const uint32_t h = threadIdx.x & (kCoop - 1);
+            f3 so[kCoop], sd[kCoop];
+            bool sa[kCoop];
+            float bt[kCoop];
+            int bk[kCoop];
+            uint32_t summary[kCoop];
+            exchange_rays<kCoop>(o, d, alive, so, sd, sa);
+            if (!kMulti) {
+                sweep_masks_packed2<kCoop, kCoop, kTraceBlock>(smem_u32(s_tile0) + h * 32u, n, h, smem_u32(s_mask), so, sd,
+                                                               summary);
+                walk_candidates_perm<kCoop, kCoop, kTraceBlock>(s_tile1, h, s_mask, so, sd, sa, summary, bt, bk);
+            } else {
+#pragma unroll
+                for (int q = 0; q < kCoop; ++q) {
+                    bt[q] = __int_as_float(0x7f800000);
+                    bk[q] = -1;
                 }
-                const float4* tile = (t & 1u) ? s_tile1 : s_tile0;
-                if (t & 1u) { mbar_wait(&s_bar[1], bar_phase1); bar_phase1 ^= 1u; }
-                else { mbar_wait(&s_bar[0], bar_phase0); bar_phase0 ^= 1u; }
-                sweep_tile<1, kSweepPacked, kCoop, kTraceBlock>(tile, nullptr, cnt, base, s_mask, oa, da, aa, bta, bka);
-                __syncthreads();  // the buffer may be overwritten by the prefetch issued in the next iteration
+                if (threadIdx.x == 0) {  // prologue: tile 0 -> buffer 0
+                    const uint32_t cnt = n_stage < kTileSpheres ? n_stage : kTileSpheres;
+                    mbar_arrive_expect_tx(&s_bar[0], cnt * 16u);
+                    tma_bulk_g2s(s_tile0, g_src, cnt * 16u, &s_bar[0]);
+                }
+                for (uint32_t t = 0; t < n_tiles; ++t) {
+                    const uint32_t base = t * kTileSpheres;
+                    const uint32_t cnt = n - base < kTileSpheres ? n - base : kTileSpheres;
+                    if (threadIdx.x == 0 && t + 1u < n_tiles) {  // prefetch tile t+1 into the other buffer
+                        const uint32_t nb = base + kTileSpheres;
+                        const uint32_t ncnt = n_stage - nb < kTileSpheres ? n_stage - nb : kTileSpheres;
+                        unsigned long long* bar = &s_bar[(t + 1u) & 1u];
+                        mbar_arrive_expect_tx(bar, ncnt * 16u);
+                        tma_bulk_g2s((t & 1u) ? s_tile0 : s_tile1, g_src + nb, ncnt * 16u, bar);
+                    }
+                    const uint32_t tile_lane = smem_u32((t & 1u) ? s_tile1 : s_tile0) + h * 32u;
+                    if (t & 1u) { mbar_wait(&s_bar[1], bar_phase1); bar_phase1 ^= 1u; }
+                    else { mbar_wait(&s_bar[0], bar_phase0); bar_phase0 ^= 1u; }
+                    sweep_masks_packed2<kCoop, kCoop, kTraceBlock>(tile_lane, cnt, h, smem_u32(s_mask), so, sd, summary);
+                    walk_candidates_pairs<kCoop, kCoop, kTraceBlock>(tile_lane, h, smem_u32(s_mask), base, so, sd, sa,
+                                                                     summary, bt, bk);
+                    __syncthreads();  // the buffer may be overwritten by the prefetch issued in the next iteration
+                }
             }
-            best_t = bta[0];
-            best_k = bka[0];
+            merge_partial_hits<kCoop>(bt, bk, best_t, best_k);
         }
     }
     // ray-segment statistics: one atomic per warp

@@ -1,5 +1,5 @@
 """One render of scene_random_spheres through the C-ABI (for ncu captures).
-Usage: python tools/one_render.py W spp depth [rays] [sweep] [reps] [half_extent] [coop] [mode]"""
+Usage: python tools/one_render.py W spp depth [rays] [sweep] [reps] [half_extent] [coop] [mode] [tail]"""
 import sys
 from pathlib import Path
 
@@ -14,6 +14,7 @@ reps = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 half = int(sys.argv[7]) if len(sys.argv) > 7 else 11
 coop = int(sys.argv[8]) if len(sys.argv) > 8 else 0
 mode = int(sys.argv[9]) if len(sys.argv) > 9 else 0
+tail = int(sys.argv[10]) if len(sys.argv) > 10 else 0
 R.reseed()
 scene = R.flatten_scene(R.scene_random_spheres(half_extent=half))
 with R.Renderer([0]) as r:
@@ -21,6 +22,7 @@ with R.Renderer([0]) as r:
     r.set_option(R.RTW_OPT_SWEEP, sweep)
     r.set_option(R.RTW_OPT_COOP, coop)
     r.set_option(R.RTW_OPT_MODE, mode)
+    r.set_option(R.RTW_OPT_TAIL, tail)
     r.set_scene(scene)
     for _ in range(reps):
         r.render(R.t_cam1(), W, spp, max_depth=depth, seed=1)

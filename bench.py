@@ -321,14 +321,17 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args).format(n=n_spheres), "l2": "flushed between steps (256 MiB write)",
                        "parallelism": f"rows interleaved over {G} GPU(s), one NCCL gather" if G > 1 else "1 GPU",
-                       "kernel": "fused persistent trace (packed FP32x2 mask sweep) + resolve"},
+                       "kernel": "fused persistent trace, unified tail (packed FP32x2 mask sweep, cooperative rejection "
+                                 "sampling) + resolve"},
             "paths_per_step": W * H * spp, "ray_segments_per_step": segs_per_step,
             "segments_per_path": segs_per_step / (W * H * spp), "Mpaths_per_s": W * H * spp / (ms_per_step * 1e-3) / 1e6,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": scene_bytes * G,
                     "d2h_bytes_per_step": image_bytes, "steps": e2e_steps},
-            "gpu_launches": (2 * G + (1 if G > 1 else 0)) * args.steps,
+            # kernels of librtw_b200.so launched inside the timed region: per rank and step the u/v table kernel, the
+            # fused trace kernel and the resolve kernel (rtw_stats.kernel_launches), plus one assemble on rank 0 for G > 1
+            "gpu_launches": (int(stats["kernel_launches"]) * G + (1 if G > 1 else 0)) * args.steps,
             "roofline": {
-                "bound": "fp32", "kernel": "fused_trace_kernel",
+                "bound": "fp32", "kernel": "fused_trace2_kernel",
                 "achieved": achieved_instr, "peak": fp32_peak / 1e12,
                 "unit": "T FP32 instr/s per GPU (11 per ray-sphere test)",
                 "frac": achieved_instr / (fp32_peak / 1e12),
@@ -354,10 +357,10 @@ def run_ours(args):
 
 def measured_dram_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r01_trace_kernel_full_metrics.csv; per launch, 1920x1080 slice).  None when the file is missing."""
+    (profiles/r01_unified_trace_kernel_full_metrics.csv; per launch, 1920x1080 slice).  None when the file is missing."""
     try:
         vals = {}
-        for line in (ROOT / "profiles" / "r01_trace_kernel_full_metrics.csv").read_text().splitlines():
+        for line in (ROOT / "profiles" / "r01_unified_trace_kernel_full_metrics.csv").read_text().splitlines():
             parts = line.split(",")
             if len(parts) == 3 and parts[0].startswith("dram__bytes_"):
                 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(parts[1], None)

@@ -94,6 +94,12 @@ typedef struct rtw_ctx rtw_ctx;
 #define RTW_OPT_COOP 7            /* lanes sharing sphere loads in the packed sweep: 1, 2 or 4 (0 = default) */
 #define RTW_OPT_TAIL 8            /* RTW_TAIL_*: layout of the per-bounce work after the sweep (RTW_MODE_FUSED) */
 
+#define RTW_OPT_WALK 9            /* RTW_WALK_*: candidate resolution after the sweep (RTW_TAIL_UNIFIED, lists <= 1024) */
+
+#define RTW_WALK_DEFAULT 0        /* library default (the fastest measured)                           */
+#define RTW_WALK_SLOTS 1          /* a lane resolves, slot by slot, the candidates it found; partial hits merged by shuffle */
+#define RTW_WALK_OWN_RAY 2        /* a lane resolves all candidates of its own ray, reading its partners' masks */
+
 #define RTW_TAIL_DEFAULT 0        /* library default (the fastest measured)                           */
 #define RTW_TAIL_SPLIT 1          /* regenerate / shade each run by the lanes in that state            */
 #define RTW_TAIL_UNIFIED 2        /* one Philox block, cooperative rejection sampling and shared normalize for

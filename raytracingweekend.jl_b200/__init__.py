@@ -11,7 +11,7 @@ The directory name contains a dot, so import it through the repo-root alias modu
 """
 from ._lib import (EXPORTED_SYMBOLS, LIB_PATH, RTW_MODE_CTA_WAVEFRONT, RTW_MODE_FUSED, RTW_MODE_WAVEFRONT, RTW_OPT_BLOCKS_PER_SM,
                    RTW_OPT_COLLECT_TIMING, RTW_OPT_COOP, RTW_OPT_MODE, RTW_OPT_RAYS_PER_LANE, RTW_OPT_STRIP, RTW_OPT_SWEEP,
-                   RTW_OPT_TAIL, RTW_TAIL_DEFAULT, RTW_TAIL_SPLIT, RTW_TAIL_UNIFIED, RtwError, rtw_camera, rtw_stats)
+                   RTW_OPT_TAIL, RTW_OPT_WALK, RTW_WALK_DEFAULT, RTW_WALK_OWN_RAY, RTW_WALK_SLOTS, RTW_TAIL_DEFAULT, RTW_TAIL_SPLIT, RTW_TAIL_UNIFIED, RtwError, rtw_camera, rtw_stats)
 from . import sharding
 from .api import DEFAULT_MAX_DEPTH, DEFAULT_SEED, Renderer, render
 from .host import (TRNG, Camera, Dielectric, HittableList, Lambertian, Metal, Sphere, Vec3, Xoroshiro128Plus,

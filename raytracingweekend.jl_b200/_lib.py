@@ -46,6 +46,10 @@ RTW_OPT_SWEEP = 6
 RTW_OPT_COOP = 7
 RTW_OPT_TAIL = 8
 
+RTW_OPT_WALK = 9
+RTW_WALK_DEFAULT = 0
+RTW_WALK_SLOTS = 1
+RTW_WALK_OWN_RAY = 2
 RTW_TAIL_DEFAULT = 0
 RTW_TAIL_SPLIT = 1
 RTW_TAIL_UNIFIED = 2

@@ -63,6 +63,7 @@ struct rtw_ctx {
     int sweep = 0;          // 0 = default
     int coop = 0;           // 0 = default
     int tail = 0;           // RTW_TAIL_*; 0 = default
+    int walk = 0;           // RTW_WALK_*; 0 = default
     int blocks_per_sm = 0;
     int collect_timing = 1;
 };
@@ -249,7 +250,7 @@ int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, in
                     p.rk[2 * r] = p.key0 + r * rtw::kPhiloxW0;
                     p.rk[2 * r + 1] = p.key1 + r * rtw::kPhiloxW1;
                 }
-                RTW_CUDA(ctx, rtw::launch_fused_trace2(p, ds.num_sms, ctx->blocks_per_sm, coop, stream, &li));
+                RTW_CUDA(ctx, rtw::launch_fused_trace2(p, ds.num_sms, ctx->blocks_per_sm, coop, ctx->walk, stream, &li));
             } else {
                 RTW_CUDA(ctx, rtw::launch_fused_trace(p, ds.num_sms, ctx->blocks_per_sm, rays, sweep, coop, stream, &li));
             }
@@ -560,6 +561,11 @@ int rtw_set_option(rtw_ctx* ctx, int option, int64_t value) {
             if (value != RTW_TAIL_DEFAULT && value != RTW_TAIL_SPLIT && value != RTW_TAIL_UNIFIED)
                 return fail(ctx, RTW_E_INVALID_ARG, "unknown tail variant");
             ctx->tail = (int)value;
+            return RTW_OK;
+        case RTW_OPT_WALK:
+            if (value != RTW_WALK_DEFAULT && value != RTW_WALK_SLOTS && value != RTW_WALK_OWN_RAY)
+                return fail(ctx, RTW_E_INVALID_ARG, "unknown walk variant");
+            ctx->walk = (int)value;
             return RTW_OK;
         case RTW_OPT_BLOCKS_PER_SM:
             if (value < 0 || value > 32) return fail(ctx, RTW_E_INVALID_ARG, "blocks_per_sm must be in 0..32");

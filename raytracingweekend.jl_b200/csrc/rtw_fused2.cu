@@ -206,6 +206,73 @@ __device__ __forceinline__ void sweep_masks_packed2(uint32_t tile_lane, uint32_t
     }
 }
 
+// Candidate resolution, transposed: every lane walks ALL candidates of ITS OWN ray -- its own slot-0 mask words and
+// the slot-q words of its group partners lane^q, read straight from their shared-memory slices -- in one loop with
+// the ray in registers; no per-slot loops, no merge of partial results.  The candidates of a ray then arrive out of
+// list order (the partners' sphere subsets interleave), so the closest hit is taken in its order-independent form:
+// the root a sphere offers is the first one >= tmin (src/hit.jl:23-28: near root, else far root -- which one does
+// not depend on the running closest t, because far >= near), the winner is the smallest such root and equal roots go
+// to the larger list index (src/hit.jl:24,26 are inclusive, so the sequential sweep lets the later sphere win).
+__device__ __forceinline__ uint32_t perm_code_to_index(uint32_t code, uint32_t coop) {
+    // code = (c*coop + h)*32 + j  ->  list index c*32*coop + 2*((j>>1)*coop + h) + (j&1)
+    const uint32_t j = code & 31u, ch = code >> 5;
+    const uint32_t c = ch / coop, h = ch - c * coop;
+    return c * (32u * coop) + 2u * ((j >> 1) * coop + h) + (j & 1u);
+}
+
+template <int kCoop, int kBlock>
+__device__ __forceinline__ void walk_own_ray_perm(const float4* __restrict__ aos_perm, const uint32_t* s_mask_base,
+                                                  const f3 o, const f3 d, const bool alive,
+                                                  const uint32_t (&summary)[kCoop], float& best_t, int& best_k) {
+    const float tmin = 1e-4f;  // T(1e-4), src/ray_color.jl:19
+    constexpr uint32_t kW = 32u / kCoop;  // summary bits (super-chunks) per slot: a list tile holds <= kW super-chunks
+    const uint32_t tid = threadIdx.x, h = tid & (kCoop - 1);
+    __syncwarp();  // the partners' mask words are visible
+    uint32_t sum = summary[0];
+#pragma unroll
+    for (int q = 1; q < kCoop; ++q) sum |= __shfl_xor_sync(kFullMask, summary[q], q) << (q * kW);
+    if (!alive) sum = 0u;
+    const uint32_t a_base = smem_u32(aos_perm), m_base = smem_u32(s_mask_base);
+    uint32_t cand = 0u, a31 = 0u, code31 = 0u;
+    float bt = __int_as_float(0x7f800000);
+    uint32_t bcode = 0xffffffffu;
+    for (;;) {
+        if (cand == 0u) {
+            if (sum == 0u) break;
+            const uint32_t w = (uint32_t)__ffs((int)sum) - 1u;
+            sum &= sum - 1u;
+            const uint32_t q = w / kW, c = w & (kW - 1u);
+            cand = ~lds32(m_base + ((c * kCoop + q) * kBlock + (tid ^ q)) * 4u);  // lane^q tested my ray in its slot q
+            code31 = (c * kCoop + (h ^ q)) * 32u + 31u;
+            a31 = a_base + code31 * 16u;
+        }
+        const uint32_t p = bfind_u32(cand);
+        cand &= low_mask(p);
+        const float4 s = lds128(a31 - 16u * p);
+        // scalar redo of src/hit.jl:13-18: bit-identical to the packed values of the sweep
+        const float ocx = o.x - s.x, ocy = o.y - s.y, ocz = o.z - s.z;
+        const float hb = fmaf(ocz, d.z, fmaf(ocy, d.y, ocx * d.x));
+        const float cq = fmaf(-s.w, s.w, fmaf(ocz, ocz, fmaf(ocy, ocy, ocx * ocx)));
+        // Sphere entirely behind the origin (half_b > 0 and origin outside): sqrt(disc) <= half_b in IEEE
+        // arithmetic, so both roots are <= 0 < tmin and src/hit.jl:24-28 rejects them -- skip the square root.
+        if (hb > 0.0f && cq > 0.0f) continue;
+        const float sq = __fsqrt_rn(fmaf(hb, hb, -cq));
+        const float r1 = -hb - sq, r2 = -hb + sq;  // src/hit.jl:23, 25
+        const float t = r1 < tmin ? r2 : r1;       // the first root >= tmin, if any
+        if (t < tmin) continue;
+        const uint32_t code = code31 - p;
+        if (t < bt) {
+            bt = t;
+            bcode = code;
+        } else if (t == bt && bcode != 0xffffffffu &&
+                   perm_code_to_index(code, kCoop) > perm_code_to_index(bcode, kCoop)) {
+            bcode = code;
+        }
+    }
+    best_t = bt;
+    best_k = bcode != 0xffffffffu ? (int)perm_code_to_index(bcode, kCoop) : -1;
+}
+
 // Candidate resolution straight from a pair-layout tile (streamed lists: no lane-order copy in shared memory).
 // `tile_lane` = address of this lane's first pair of super-chunk 0, k_base = list index of the tile's first sphere;
 // best_t / best_k carry the closest hit over the tiles walked so far (tiles come in list order, so ties still go to
@@ -297,7 +364,7 @@ __device__ __forceinline__ void merge_partial_hits(const float (&bt)[kCoop], con
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------
-template <bool kMulti, int kCoop>
+template <bool kMulti, int kCoop, bool kOwnWalk>
 __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __grid_constant__ TraceParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_bar[2];
@@ -572,7 +639,11 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
             if (!kMulti) {
                 sweep_masks_packed2<kCoop, kCoop, kTraceBlock>(smem_u32(s_tile0) + h * 32u, n, h, smem_u32(s_mask), so, sd,
                                                                summary);
-                walk_candidates_perm<kCoop, kCoop, kTraceBlock>(s_tile1, h, s_mask, so, sd, sa, summary, bt, bk);
+                if (kOwnWalk) {
+                    walk_own_ray_perm<kCoop, kTraceBlock>(s_tile1, s_mask - threadIdx.x, o, d, alive, summary, best_t, best_k);
+                } else {
+                    walk_candidates_perm<kCoop, kCoop, kTraceBlock>(s_tile1, h, s_mask, so, sd, sa, summary, bt, bk);
+                }
             } else {
 #pragma unroll
                 for (int q = 0; q < kCoop; ++q) {
@@ -603,7 +674,7 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
                     __syncthreads();  // the buffer may be overwritten by the prefetch issued in the next iteration
                 }
             }
-            merge_partial_hits<kCoop>(bt, bk, best_t, best_k);
+            if (kMulti || !kOwnWalk) merge_partial_hits<kCoop>(bt, bk, best_t, best_k);
         }
     }
     // ray-segment statistics: one atomic per warp
@@ -621,10 +692,10 @@ __global__ void __launch_bounds__(256) uv_table_kernel(int W, int H, float* __re
     if (t < H) v_tab[t] = __fdiv_rn((float)(H - 1 - t), (float)H);
 }
 
-template <bool kMulti, int kCoop>
+template <bool kMulti, int kCoop, bool kOwnWalk>
 cudaError_t launch_variant2(const TraceParams& p, int num_sms, int blocks_per_sm_override, cudaStream_t stream,
                             LaunchInfo* info) {
-    auto kern = fused_trace2_kernel<kMulti, kCoop>;
+    auto kern = fused_trace2_kernel<kMulti, kCoop, kOwnWalk>;
     constexpr uint32_t kGran = 32u * kCoop;
     const uint32_t tile_cap = kMulti ? kTileSpheres : ((p.n_spheres + kGran - 1u) / kGran) * kGran;
     const uint32_t chunks = tile_cap / 32u;  // mask words per lane: (tile_cap / kGran) super-chunks x kCoop slots
@@ -674,15 +745,20 @@ cudaError_t launch_uv_tables(int W, int H, float* u_tab, float* v_tab, cudaStrea
     return cudaGetLastError();
 }
 
-cudaError_t launch_fused_trace2(const TraceParams& p, int num_sms, int blocks_per_sm_override, int coop,
+cudaError_t launch_fused_trace2(const TraceParams& p, int num_sms, int blocks_per_sm_override, int coop, int walk,
                                 cudaStream_t stream, LaunchInfo* info) {
     const bool multi = p.n_spheres > kTileSpheres;
-    if (coop == 4) {
-        return multi ? launch_variant2<true, 4>(p, num_sms, blocks_per_sm_override, stream, info)
-                     : launch_variant2<false, 4>(p, num_sms, blocks_per_sm_override, stream, info);
+    if (multi) {
+        return coop == 4 ? launch_variant2<true, 4, false>(p, num_sms, blocks_per_sm_override, stream, info)
+                         : launch_variant2<true, 2, false>(p, num_sms, blocks_per_sm_override, stream, info);
     }
-    return multi ? launch_variant2<true, 2>(p, num_sms, blocks_per_sm_override, stream, info)
-                 : launch_variant2<false, 2>(p, num_sms, blocks_per_sm_override, stream, info);
+    if (walk == 0) walk = coop == 4 ? 2 : 1;  // measured: per-slot walks win with 2 cooperating lanes, own-ray with 4
+    if (walk == 1) {  // per-slot candidate walks + merge
+        return coop == 4 ? launch_variant2<false, 4, false>(p, num_sms, blocks_per_sm_override, stream, info)
+                         : launch_variant2<false, 2, false>(p, num_sms, blocks_per_sm_override, stream, info);
+    }
+    return coop == 4 ? launch_variant2<false, 4, true>(p, num_sms, blocks_per_sm_override, stream, info)
+                     : launch_variant2<false, 2, true>(p, num_sms, blocks_per_sm_override, stream, info);
 }
 
 }  // namespace rtw

@@ -74,7 +74,8 @@ cudaError_t launch_fused_trace(const TraceParams& p, int num_sms, int blocks_per
                                int sweep, int coop, cudaStream_t stream, LaunchInfo* info);
 // RTW_TAIL_UNIFIED (rtw_fused2.cu): packed sweep, one path per lane, coop = 2 or 4; needs geom_perm / u_tab / v_tab /
 // div_* of TraceParams
-cudaError_t launch_fused_trace2(const TraceParams& p, int num_sms, int blocks_per_sm_override, int coop,
+// walk: 1 = per-slot walks + merge, 2 = every lane resolves the candidates of its own ray (transposed), 0 = default
+cudaError_t launch_fused_trace2(const TraceParams& p, int num_sms, int blocks_per_sm_override, int coop, int walk,
                                 cudaStream_t stream, LaunchInfo* info);
 cudaError_t launch_uv_tables(int W, int H, float* u_tab, float* v_tab, cudaStream_t stream);
 MagicDiv make_magic_div(uint32_t d);

@@ -116,6 +116,35 @@ def test_tail_variants_on_reference_scenes_and_odd_shapes(rtw, oracle, renderer,
         renderer.set_option(rtw.RTW_OPT_TAIL, 0)
 
 
+@pytest.mark.parametrize("coop,walk", [(2, 1), (4, 1), (2, 2), (4, 2)])
+def test_candidate_walk_variants(rtw, oracle, renderer, scenes, coop, walk):
+    # RTW_WALK_SLOTS: per-slot walks in list order + merge; RTW_WALK_OWN_RAY: each lane resolves its own ray from its
+    # partners' masks, closest hit in order-independent form (min t, ties to the larger list index).  Same bits on the
+    # random scene, on coincident spheres (ties across cooperating lanes) and on ragged list sizes.
+    g, m, k = scenes["random"]
+    tie_geom = np.array([[0, 0, -1, 0.5]] * 7 + [[0, -100.5, -1, 100]], np.float32)
+    tie_mat = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [1, 1, 0, 0], [0, 1, 1, 0], [1, 0, 1, 0], [0.2, 0.9, 0.4, 0],
+                        [0.5, 0.5, 0.5, 0]], np.float32)
+    tie = (tie_geom, tie_mat, np.zeros(8, np.uint32))
+    cases = [((g, m, k), rtw.t_cam1(), 200, 16, 16, 3), (tie, rtw.t_default_cam(), 96, 8, 8, 1)]
+    for n in (5, 63, 65, 129, 130, 257):
+        order = np.concatenate([[0], np.arange(len(k) - 3, len(k)), np.arange(1, len(k) - 3)])[:n]
+        cases.append(((g[order].copy(), m[order].copy(), k[order].copy()), rtw.t_cam1(), 64, 4, 12, 11))
+    renderer.set_option(rtw.RTW_OPT_COOP, coop)
+    renderer.set_option(rtw.RTW_OPT_WALK, walk)
+    renderer.set_option(rtw.RTW_OPT_TAIL, rtw.RTW_TAIL_UNIFIED)
+    try:
+        for scene, cam, W, spp, depth, seed in cases:
+            img = renderer.render(cam, W, spp, max_depth=depth, seed=seed, scene=scene)
+            segs = renderer.last_stats["ray_segments"]
+            ref, _, ost = oracle.render(*scene, cam.as_array(), W, spp, max_depth=depth, seed=seed)
+            _compare(img, ref)
+            assert segs == ost["ray_segments"], (len(scene[2]), coop, walk)
+    finally:
+        for opt in (rtw.RTW_OPT_COOP, rtw.RTW_OPT_WALK, rtw.RTW_OPT_TAIL):
+            renderer.set_option(opt, 0)
+
+
 def test_golden_fixture_cfg1(rtw, renderer, scenes):
     # committed fixture (tests/golden/make_golden.py): the CUDA path reproduces it without the oracle at hand
     from pathlib import Path

@@ -26,9 +26,12 @@ def main():
             print(f"fp32 peak variant {v}: {rate / 1e12:.2f} T lane-instr/s ({ms:.3f} ms)", flush=True)
         r.set_scene(scene)
         base = None
-        for rays, sweep, bps, coop, tail in [(1, 1, 0, 1, 1), (1, 2, 0, 1, 1), (1, 3, 0, 1, 1), (2, 3, 0, 1, 1), (1, 3, 0, 2, 1),
-                                             (1, 3, 0, 4, 1), (1, 3, 0, 2, 2), (1, 3, 0, 4, 2), (1, 3, 2, 2, 2), (1, 3, 2, 4, 2)]:
+        full = len(sys.argv) > 2 and sys.argv[2] == "all"
+        legacy = [(1, 1, 0, 1, 1, 0), (1, 2, 0, 1, 1, 0), (1, 3, 0, 1, 1, 0), (2, 3, 0, 1, 1, 0), (1, 3, 0, 4, 1, 0)] if full else []
+        for rays, sweep, bps, coop, tail, walk in legacy + [(1, 3, 0, 2, 1, 0), (1, 3, 0, 2, 2, 1), (1, 3, 0, 4, 2, 1),
+                                                            (1, 3, 0, 2, 2, 2), (1, 3, 0, 4, 2, 2), (1, 3, 2, 4, 2, 2)]:
             r.set_option(R.RTW_OPT_TAIL, tail)
+            r.set_option(R.RTW_OPT_WALK, walk)
             r.set_option(R.RTW_OPT_RAYS_PER_LANE, rays)
             r.set_option(R.RTW_OPT_SWEEP, sweep)
             r.set_option(R.RTW_OPT_BLOCKS_PER_SM, bps)
@@ -44,7 +47,7 @@ def main():
             same = bool(np.array_equal(base, img))
             mrays = best["ray_segments"] / best["ms_trace"] / 1e3
             fp32 = best["sphere_tests"] * 11 / (best["ms_trace"] * 1e-3) / 1e12
-            rec = {"rays_per_lane": rays, "sweep": sweep, "blocks_per_sm": bps, "coop": coop, "tail": tail, "ms_trace": best["ms_trace"],
+            rec = {"rays_per_lane": rays, "sweep": sweep, "blocks_per_sm": bps, "coop": coop, "tail": tail, "walk": walk, "ms_trace": best["ms_trace"],
                    "Mrays_s": mrays, "fp32_Tinstr_s": fp32, "segments_per_path": best["ray_segments"] / best["paths"],
                    "identical_image": same, "n_spheres": n}
             out["variants"].append(rec)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RTW_ABI_VERSION 1
+#define RTW_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define RTW_API __attribute__((visibility("default")))
@@ -39,6 +39,8 @@ extern "C" {
 #define RTW_E_NO_SCENE (-3)      /* render called before rtw_set_scene                               */
 #define RTW_E_UNSUPPORTED (-4)   /* e.g. unknown material kind, unknown option                       */
 #define RTW_E_INTERNAL (-5)
+#define RTW_E_IO (-6)            /* a file could not be opened / read / written                       */
+#define RTW_E_FORMAT (-7)        /* not a .rtwscene file, or its checksum does not match              */
 
 /* Material{T} subtypes, flattened (src/material.jl:3-5 Lambertian, :25-29 Metal, :37-39 Dielectric) */
 #define RTW_LAMBERTIAN 0u
@@ -193,6 +195,61 @@ RTW_API int rtw_last_stats(rtw_ctx* ctx, int device_slot, rtw_stats* stats);
  */
 RTW_API int rtw_assemble_tiles_device(rtw_ctx* ctx, int device_slot, const float* d_tiles, int n_tiles, int image_width,
                               float* d_out_rgb, void* stream);
+
+/* ---- progressive rendering ------------------------------------------------------------------- */
+
+/*
+ * render() split into passes over the samples.  Every random draw is addressed by (pixel, sample, event, draw) and
+ * the accumulator is an integer sum, so the image after rtw_accumulate(0, a) + rtw_accumulate(a, b) is bit-identical
+ * to rtw_render with a + b samples (src/render.jl:29-40 run in one go).  Uses: previews of a 1000-spp render,
+ * checkpoint / resume (rtw_accumulator_read / _write), time-sliced rendering.
+ *
+ * rtw_accumulate adds samples sample_first .. sample_first + sample_count - 1 of every pixel to the accumulators held
+ * by the context.  n_samples_total = the number of samples the finished image will hold: it fixes the fixed-point
+ * scale, so it must be the same in every call of one image.  sample_first == 0 starts a new image (accumulators
+ * zeroed); otherwise it must equal the number of samples accumulated so far, with the same image_width.
+ * rtw_render* discards a progressive image.
+ */
+RTW_API int rtw_accumulate(rtw_ctx* ctx, const rtw_camera* cam, int image_width, int sample_first, int sample_count,
+                           int n_samples_total, int max_depth, uint64_t seed, rtw_stats* stats);
+
+/* sqrt(accumulated sum / samples accumulated so far) into a HOST buffer, layout as rtw_render (src/render.jl:40). */
+RTW_API int rtw_resolve(rtw_ctx* ctx, float* out_rgb);
+
+/*
+ * The same image as 8-bit RGB, row-major, top row first (H*W*3 bytes, HOST buffer): what Images.jl writes for
+ * save("x.png", img) -- every channel through clamp01nan, then N0f8: round(x * 255).  (The reference itself never
+ * saves an image: README.md:138,170.)
+ */
+RTW_API int rtw_resolve_rgb8(rtw_ctx* ctx, uint8_t* out_rgb8);
+
+/* state of the progressive image: width, samples accumulated, samples planned (all 0 when there is none) */
+RTW_API int rtw_progress(rtw_ctx* ctx, int* image_width, int* samples_done, int* samples_total);
+
+/*
+ * Checkpoint / resume: the raw accumulators of the progressive image, H*W*4 int64 values, row-major
+ * [row][col][r,g,b,unused] fixed-point sums (HOST buffers; n_values must be H*W*4).  rtw_accumulator_write installs
+ * a saved state (in a context with the same or a different device count) so that rtw_accumulate can continue at
+ * sample `samples_done`.
+ */
+RTW_API int rtw_accumulator_read(rtw_ctx* ctx, int64_t* out, uint64_t n_values);
+RTW_API int rtw_accumulator_write(rtw_ctx* ctx, const int64_t* in, uint64_t n_values, int image_width, int samples_done,
+                                  int samples_total);
+
+/* ---- image and scene files (host side; no device needed) ---------------------------------------- */
+
+/* binary PPM (P6) / PNG (8-bit RGB, stored deflate blocks) of a row-major 8-bit image, top row first */
+RTW_API int rtw_write_ppm(const char* path, const uint8_t* rgb8, int width, int height);
+RTW_API int rtw_write_png(const char* path, const uint8_t* rgb8, int width, int height);
+
+/*
+ * .rtwscene: the flattened HittableList exactly as it crosses rtw_set_scene -- "RTWSCN01", u32 n, u32 0 (Float32),
+ * geom4[n][4], mat4[n][4], kind[n], CRC-32 -- little endian.  One fixture format for the Julia shim, the Python
+ * harness, the oracle and the kernels.  rtw_scene_load with capacity 0 only reports n_spheres.
+ */
+RTW_API int rtw_scene_save(const char* path, const float* geom4, const float* mat4, const uint32_t* kind, uint32_t n_spheres);
+RTW_API int rtw_scene_load(const char* path, float* geom4, float* mat4, uint32_t* kind, uint32_t capacity,
+                           uint32_t* n_spheres);
 
 /* ---- roofline denominator --------------------------------------------------------------------- */
 

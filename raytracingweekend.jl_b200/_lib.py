@@ -28,7 +28,19 @@ EXPORTED_SYMBOLS = (
     "rtw_last_stats",
     "rtw_assemble_tiles_device",
     "rtw_measure_fp32_peak",
+    "rtw_accumulate",
+    "rtw_resolve",
+    "rtw_resolve_rgb8",
+    "rtw_progress",
+    "rtw_accumulator_read",
+    "rtw_accumulator_write",
+    "rtw_write_ppm",
+    "rtw_write_png",
+    "rtw_scene_save",
+    "rtw_scene_load",
 )
+
+RTW_ABI_VERSION = 2
 
 RTW_OK = 0
 RTW_E_INVALID_ARG = -1
@@ -36,6 +48,8 @@ RTW_E_NO_DEVICE = -2
 RTW_E_NO_SCENE = -3
 RTW_E_UNSUPPORTED = -4
 RTW_E_INTERNAL = -5
+RTW_E_IO = -6
+RTW_E_FORMAT = -7
 
 RTW_OPT_MODE = 1
 RTW_OPT_STRIP = 2
@@ -155,6 +169,27 @@ def load() -> C.CDLL:
     lib.rtw_assemble_tiles_device.argtypes = [vp, i32, vp, i32, i32, vp, vp]
     lib.rtw_measure_fp32_peak.restype = i32
     lib.rtw_measure_fp32_peak.argtypes = [vp, i32, i32, C.POINTER(C.c_double), fp]
+    u8p, i64p, i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int64), C.POINTER(i32)
+    lib.rtw_accumulate.restype = i32
+    lib.rtw_accumulate.argtypes = [vp, C.POINTER(rtw_camera), i32, i32, i32, i32, i32, u64, C.POINTER(rtw_stats)]
+    lib.rtw_resolve.restype = i32
+    lib.rtw_resolve.argtypes = [vp, fp]
+    lib.rtw_resolve_rgb8.restype = i32
+    lib.rtw_resolve_rgb8.argtypes = [vp, u8p]
+    lib.rtw_progress.restype = i32
+    lib.rtw_progress.argtypes = [vp, i32p, i32p, i32p]
+    lib.rtw_accumulator_read.restype = i32
+    lib.rtw_accumulator_read.argtypes = [vp, i64p, u64]
+    lib.rtw_accumulator_write.restype = i32
+    lib.rtw_accumulator_write.argtypes = [vp, i64p, u64, i32, i32, i32]
+    lib.rtw_write_ppm.restype = i32
+    lib.rtw_write_ppm.argtypes = [C.c_char_p, u8p, i32, i32]
+    lib.rtw_write_png.restype = i32
+    lib.rtw_write_png.argtypes = [C.c_char_p, u8p, i32, i32]
+    lib.rtw_scene_save.restype = i32
+    lib.rtw_scene_save.argtypes = [C.c_char_p, fp, fp, u32p, u32]
+    lib.rtw_scene_load.restype = i32
+    lib.rtw_scene_load.argtypes = [C.c_char_p, fp, fp, u32p, u32, u32p]
     _lib = lib
     return lib
 
@@ -173,6 +208,8 @@ def check(ctx, status: int) -> None:
             RTW_E_NO_DEVICE: "no CUDA device visible (the hot path has no CPU fallback)",
             RTW_E_NO_SCENE: "no scene set",
             RTW_E_UNSUPPORTED: "unsupported",
+            RTW_E_IO: "file could not be opened / read / written",
+            RTW_E_FORMAT: "not a .rtwscene file, or its checksum does not match",
             RTW_E_INTERNAL: "internal error",
         }.get(status, "CUDA error" if status > 0 else "error")
     raise RtwError(status, msg)

@@ -110,6 +110,55 @@ class Renderer:
         self.last_stats = st.as_dict()
         return out.transpose(1, 0, 2)
 
+    # -- progressive rendering: render() split into passes over the samples (bit-identical to one render)
+    def accumulate(self, cam: Camera, image_width: int, sample_first: int, sample_count: int, n_samples_total: int, *,
+                   max_depth: int = DEFAULT_MAX_DEPTH, seed: int = DEFAULT_SEED) -> dict:
+        """Adds samples [sample_first, sample_first + sample_count) of every pixel to the accumulators held by the
+        context; sample_first == 0 starts a new image.  Returns the stats of the pass."""
+        cs = _camera_struct(cam)
+        st = rtw_stats()
+        self._check(self._lib.rtw_accumulate(self._ctx, C.byref(cs), int(image_width), int(sample_first), int(sample_count),
+                                             int(n_samples_total), int(max_depth), int(seed), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return self.last_stats
+
+    def progress(self):
+        """(image_width, samples_done, samples_total) of the progressive image; zeros when there is none."""
+        w, d, t = C.c_int(), C.c_int(), C.c_int()
+        self._check(self._lib.rtw_progress(self._ctx, C.byref(w), C.byref(d), C.byref(t)))
+        return w.value, d.value, t.value
+
+    def resolve(self) -> np.ndarray:
+        """sqrt(sum / samples so far) of the progressive image: (H, W, 3) float32 view, as render()."""
+        W, done, _ = self.progress()
+        if done < 1:
+            raise RtwError(_lib.RTW_E_INVALID_ARG, "no progressive image: call accumulate() first")
+        out = np.empty((W, image_height(W), 3), dtype=F32)
+        self._check(self._lib.rtw_resolve(self._ctx, _fp(out)))
+        return out.transpose(1, 0, 2)
+
+    def resolve_rgb8(self) -> np.ndarray:
+        """The progressive image as (H, W, 3) uint8, row-major (clamp01nan + N0f8 rounding, as Images.jl saves)."""
+        W, done, _ = self.progress()
+        if done < 1:
+            raise RtwError(_lib.RTW_E_INVALID_ARG, "no progressive image: call accumulate() first")
+        out = np.empty((image_height(W), W, 3), dtype=np.uint8)
+        self._check(self._lib.rtw_resolve_rgb8(self._ctx, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def accumulator_read(self) -> np.ndarray:
+        """Checkpoint: the raw fixed-point sums, (H, W, 4) int64 (r, g, b, unused)."""
+        W, _, _ = self.progress()
+        out = np.empty((image_height(W), W, 4), dtype=np.int64)
+        self._check(self._lib.rtw_accumulator_read(self._ctx, out.ctypes.data_as(C.POINTER(C.c_int64)), out.size))
+        return out
+
+    def accumulator_write(self, acc: np.ndarray, image_width: int, samples_done: int, samples_total: int) -> None:
+        """Resume: install saved sums so that accumulate() continues at sample `samples_done`."""
+        acc = np.ascontiguousarray(acc, dtype=np.int64)
+        self._check(self._lib.rtw_accumulator_write(self._ctx, acc.ctypes.data_as(C.POINTER(C.c_int64)), acc.size,
+                                                    int(image_width), int(samples_done), int(samples_total)))
+
     # -- device-resident variants (plain device pointers; used with torch tensors as plumbing)
     def render_rows_device(self, cam: Camera, image_width: int, n_samples: int, d_tile_ptr: int, *, max_depth: int =
                            DEFAULT_MAX_DEPTH, seed: int = DEFAULT_SEED, row_start: int = 0, row_stride: int = 1,
@@ -148,6 +197,42 @@ def _as_flat(scene):
     kind = np.ascontiguousarray(kind, dtype=np.uint32).reshape(-1)
     if not (len(geom) == len(mat) == len(kind)):
         raise ValueError("geom4, mat4 and kind must have the same length")
+    return geom, mat, kind
+
+
+# -- image and scene files (host side of the library; no device needed)
+def write_ppm(path, rgb8: np.ndarray) -> None:
+    """Binary PPM (P6) of an (H, W, 3) uint8 image."""
+    rgb8 = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    h, w, _ = rgb8.shape
+    _lib.check(None, _lib.load().rtw_write_ppm(str(path).encode(), rgb8.ctypes.data_as(C.POINTER(C.c_uint8)), w, h))
+
+
+def write_png(path, rgb8: np.ndarray) -> None:
+    """PNG (8-bit RGB) of an (H, W, 3) uint8 image."""
+    rgb8 = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    h, w, _ = rgb8.shape
+    _lib.check(None, _lib.load().rtw_write_png(str(path).encode(), rgb8.ctypes.data_as(C.POINTER(C.c_uint8)), w, h))
+
+
+def scene_save(path, scene) -> None:
+    """Writes a HittableList (or a flattened triple) as a .rtwscene file."""
+    geom, mat, kind = _as_flat(scene)
+    _lib.check(None, _lib.load().rtw_scene_save(str(path).encode(), _fp(geom), _fp(mat),
+                                                kind.ctypes.data_as(C.POINTER(C.c_uint32)), len(kind)))
+
+
+def scene_load(path):
+    """Reads a .rtwscene file; returns the flattened (geom4, mat4, kind) triple."""
+    lib = _lib.load()
+    n = C.c_uint32()
+    _lib.check(None, lib.rtw_scene_load(str(path).encode(), None, None, None, 0, C.byref(n)))
+    geom = np.zeros((n.value, 4), dtype=F32)
+    mat = np.zeros((n.value, 4), dtype=F32)
+    kind = np.zeros(n.value, dtype=np.uint32)
+    if n.value:
+        _lib.check(None, lib.rtw_scene_load(str(path).encode(), _fp(geom), _fp(mat),
+                                            kind.ctypes.data_as(C.POINTER(C.c_uint32)), n.value, C.byref(n)))
     return geom, mat, kind
 
 

@@ -41,6 +41,8 @@ struct DeviceState {
     size_t gather_cap = 0;
     float* d_image = nullptr;
     size_t image_cap = 0;
+    unsigned char* d_rgb8 = nullptr;
+    size_t rgb8_cap = 0;
     float* d_scratch = nullptr;
     unsigned char* d_wf = nullptr;  // RTW_MODE_WAVEFRONT path pool
     size_t wf_cap = 0;              // bytes
@@ -48,12 +50,20 @@ struct DeviceState {
     rtw_stats last = {};
     cudaStream_t last_stream = nullptr;
     bool last_valid = false;
+    bool last_resolved = false;  // the last enqueue included a resolve (ev[2] is meaningful)
 };
 
 }  // namespace
 
+// progressive image held in the accumulators of the context's devices (rtw_accumulate / rtw_resolve)
+struct ProgressiveState {
+    bool valid = false;
+    int W = 0, s_total = 0, s_done = 0;
+};
+
 struct rtw_ctx {
     std::mutex mu;
+    ProgressiveState prog;
     std::string err;
     std::vector<DeviceState> dev;
     uint32_t n_spheres = 0;
@@ -176,11 +186,20 @@ int wavefront_buffers(rtw_ctx* ctx, DeviceState& ds, unsigned long long n_paths,
     return RTW_OK;
 }
 
-// Enqueue trace + resolve for a row subset on one device.  Output: d_out (tile row-major, or Julia column-major).
-int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, int spp, int max_depth, uint64_t seed,
-                 int row_start, int row_stride, int column_major, float* d_out, cudaStream_t stream, bool timing) {
+// Which samples of the image a trace launch adds to the accumulator.  render(): all of them at once.  Progressive
+// passes: samples [s_first, s_first + s_count) of an image that will hold s_total samples per pixel; the fixed-point
+// scale depends on s_total only, so any split of the samples into passes sums to the same integers.
+struct PassSpec {
+    int s_first, s_count, s_total;
+    bool reset;  // zero the accumulator first
+};
+
+// Enqueue the trace of one pass for a row subset on one device (accumulates into ds.d_accum).
+int enqueue_trace(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, int max_depth, uint64_t seed,
+                  int row_start, int row_stride, const PassSpec& ps, cudaStream_t stream, bool timing) {
     const int H = rtw_image_height(W);
     const int n_rows = rows_of(H, row_start, row_stride);
+    const int spp = ps.s_count;
     RTW_CUDA(ctx, cudaSetDevice(ds.device));
     ds.last = rtw_stats{};
     ds.last.n_spheres = ctx->n_spheres;
@@ -193,15 +212,16 @@ int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, in
     if (n_rows == 0 || H == 0) return RTW_OK;
 
     const size_t npix = (size_t)n_rows * (size_t)W;
+    if (!ps.reset && npix * 4 > ds.accum_cap) return fail(ctx, RTW_E_INVALID_ARG, "no accumulator of this size to add samples to");
     int rc = grow(ctx, &ds.d_accum, &ds.accum_cap, npix * 4);
     if (rc) return rc;
     if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[0], stream));
-    RTW_CUDA(ctx, cudaMemsetAsync(ds.d_accum, 0, npix * 4 * sizeof(unsigned long long), stream));
+    if (ps.reset) RTW_CUDA(ctx, cudaMemsetAsync(ds.d_accum, 0, npix * 4 * sizeof(unsigned long long), stream));
     RTW_CUDA(ctx, cudaMemsetAsync(ds.d_counters, 0, 2 * sizeof(unsigned long long), stream));
 
-    const int fx_bits = fx_bits_for(spp);
+    const int fx_bits = fx_bits_for(ps.s_total);
     int launches = 0;
-    if (max_depth > 0) {
+    if (max_depth > 0 && spp > 0) {
         rtw::TraceParams p;
         p.cam = to_dev_camera(cam);
         p.geom = ds.d_geom;
@@ -214,6 +234,7 @@ int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, in
         p.kind = ds.d_kind;
         p.n_spheres = ctx->n_spheres;
         p.W = W; p.H = H; p.spp = spp; p.max_depth = max_depth;
+        p.sample_first = ps.s_first;
         p.key0 = (uint32_t)seed; p.key1 = (uint32_t)(seed >> 32);
         p.row_start = row_start; p.row_stride = row_stride; p.n_rows = n_rows;
         p.n_paths = (unsigned long long)npix * (unsigned long long)spp;
@@ -258,14 +279,36 @@ int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, in
         launches += li.launches;
     }
     if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[1], stream));
-    RTW_CUDA(ctx, rtw::launch_resolve(ds.d_accum, W, H, n_rows, row_start, row_stride, spp, std::ldexp(1.0, -fx_bits),
-                                      column_major, d_out, stream));
-    launches += 1;
-    if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[2], stream));
     RTW_CUDA(ctx, cudaMemcpyAsync(ds.h_counters, ds.d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                   stream));
     ds.last.kernel_launches = launches;
+    ds.last_resolved = false;
     return RTW_OK;
+}
+
+// Enqueue the resolve of a device's accumulator rows: accum / divisor -> sqrt -> Float32 (src/render.jl:40), into a
+// row-major tile or the Julia column-major image; then the counter read-back of the preceding trace.
+int enqueue_resolve(rtw_ctx* ctx, DeviceState& ds, int W, int row_start, int row_stride, int column_major, int divisor,
+                    int s_total, float* d_out, cudaStream_t stream, bool timing) {
+    const int H = rtw_image_height(W);
+    const int n_rows = rows_of(H, row_start, row_stride);
+    RTW_CUDA(ctx, cudaSetDevice(ds.device));
+    if (n_rows == 0 || H == 0) return RTW_OK;
+    RTW_CUDA(ctx, rtw::launch_resolve(ds.d_accum, W, H, n_rows, row_start, row_stride, divisor,
+                                      std::ldexp(1.0, -fx_bits_for(s_total)), column_major, d_out, stream));
+    ds.last.kernel_launches += 1;
+    if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[2], stream));
+    ds.last_resolved = true;
+    return RTW_OK;
+}
+
+// trace + resolve of a whole render() for a row subset on one device
+int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, int spp, int max_depth, uint64_t seed,
+                 int row_start, int row_stride, int column_major, float* d_out, cudaStream_t stream, bool timing) {
+    int rc = enqueue_trace(ctx, ds, cam, W, max_depth, seed, row_start, row_stride, PassSpec{0, spp, spp, true}, stream,
+                           timing);
+    if (rc) return rc;
+    return enqueue_resolve(ctx, ds, W, row_start, row_stride, column_major, spp, spp, d_out, stream, timing);
 }
 
 // after the stream has been synchronised: fill counters / timings
@@ -275,7 +318,7 @@ int finish_stats(rtw_ctx* ctx, DeviceState& ds, bool timing) {
     if (timing && ds.last.rows_rendered > 0) {
         float a = 0.f, b = 0.f;
         RTW_CUDA(ctx, cudaEventElapsedTime(&a, ds.ev[0], ds.ev[1]));
-        RTW_CUDA(ctx, cudaEventElapsedTime(&b, ds.ev[1], ds.ev[2]));
+        if (ds.last_resolved) RTW_CUDA(ctx, cudaEventElapsedTime(&b, ds.ev[1], ds.ev[2]));
         ds.last.ms_trace = a;
         ds.last.ms_resolve = b;
         ds.last.ms_total = a + b;
@@ -350,56 +393,91 @@ int set_scene_locked(rtw_ctx* ctx, const float* geom4, const float* mat4, const 
     return RTW_OK;
 }
 
-int render_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int spp, int max_depth, uint64_t seed, float* out_rgb,
-                  rtw_stats* stats, bool scene_uploaded_in_call) {
-    int rc = check_render_args(ctx, cam, W, spp, max_depth);
-    if (rc) return rc;
-    if (!out_rgb) return fail(ctx, RTW_E_INVALID_ARG, "out_rgb is NULL");
+// One pass over all devices of the context: trace (rows r -> device r mod G) and / or resolve + collect on device 0
+// + download.  render() = trace and resolve of all samples; progressive rendering = trace-only passes followed by
+// resolve-only calls (rtw_accumulate / rtw_resolve / rtw_resolve_rgb8).
+//   out_rgb  : host, Julia column-major Float32 image (or NULL)
+//   out_rgb8 : host, row-major 8-bit image, top row first (or NULL)
+int pass_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int max_depth, uint64_t seed, const PassSpec& ps, bool do_trace,
+                bool do_resolve, int divisor, float* out_rgb, uint8_t* out_rgb8, rtw_stats* stats,
+                bool scene_uploaded_in_call) {
     const int H = rtw_image_height(W);
     const int G = (int)ctx->dev.size();
     const size_t img_floats = (size_t)W * (size_t)H * 3;
     DeviceState& d0 = ctx->dev[0];
     const bool timing = ctx->collect_timing != 0;
+    int rc;
     RTW_CUDA(ctx, cudaSetDevice(d0.device));
-    rc = grow(ctx, &d0.d_image, &d0.image_cap, img_floats);
-    if (rc) return rc;
     // ev[3] = start of the call (recorded by rtw_render_scene before the upload when the scene travels with it)
     if (!scene_uploaded_in_call) RTW_CUDA(ctx, cudaEventRecord(d0.ev[3], d0.stream));
     RTW_CUDA(ctx, cudaEventRecord(d0.ev[6], d0.stream));
-    if (G == 1) {
-        rc = enqueue_rows(ctx, d0, cam, W, spp, max_depth, seed, 0, 1, 1, d0.d_image, d0.stream, timing);
-        if (rc) return rc;
-    } else {
-        const int rows_pad = (H + G - 1) / G;
-        const size_t tile_floats = (size_t)rows_pad * W * 3;
-        rc = grow(ctx, &d0.d_gather, &d0.gather_cap, tile_floats * G);
-        if (rc) return rc;
+    if (do_trace) {
         for (int g = 0; g < G; ++g) {
             DeviceState& ds = ctx->dev[g];
-            RTW_CUDA(ctx, cudaSetDevice(ds.device));
-            float* dst = d0.d_gather + tile_floats * g;
-            float* tile = dst;
-            if (g != 0) {
-                rc = grow(ctx, &ds.d_tile, &ds.tile_cap, tile_floats);
-                if (rc) return rc;
-                tile = ds.d_tile;
-            }
-            rc = enqueue_rows(ctx, ds, cam, W, spp, max_depth, seed, g, G, 0, tile, ds.stream, timing);
+            rc = enqueue_trace(ctx, ds, cam, W, max_depth, seed, g, G, ps, ds.stream, timing);
             if (rc) return rc;
-            if (g != 0) {
-                // framebuffer gather: tile -> device 0 over NVLink (peer copy on the producer's stream)
-                size_t bytes = (size_t)rows_of(H, g, G) * W * 3 * sizeof(float);
-                if (bytes) RTW_CUDA(ctx, cudaMemcpyPeerAsync(dst, d0.device, tile, ds.device, bytes, ds.stream));
-                RTW_CUDA(ctx, cudaEventRecord(ds.ev_tile, ds.stream));
-            }
         }
-        RTW_CUDA(ctx, cudaSetDevice(d0.device));
-        for (int g = 1; g < G; ++g) RTW_CUDA(ctx, cudaStreamWaitEvent(d0.stream, ctx->dev[g].ev_tile, 0));
-        RTW_CUDA(ctx, rtw::launch_assemble(d0.d_gather, G, W, H, d0.d_image, d0.stream));
+    } else {
+        for (auto& ds : ctx->dev) {  // stats of this call: nothing traced
+            ds.last = rtw_stats{};
+            ds.last.n_spheres = ctx->n_spheres;
+            ds.last.image_width = W;
+            ds.last.image_height = H;
+            ds.last_resolved = false;
+            ds.h_counters[1] = 0;
+        }
     }
+    if (do_resolve) {
+        RTW_CUDA(ctx, cudaSetDevice(d0.device));
+        rc = grow(ctx, &d0.d_image, &d0.image_cap, img_floats);
+        if (rc) return rc;
+        if (G == 1) {
+            rc = enqueue_resolve(ctx, d0, W, 0, 1, 1, divisor, ps.s_total, d0.d_image, d0.stream, timing);
+            if (rc) return rc;
+        } else {
+            const int rows_pad = (H + G - 1) / G;
+            const size_t tile_floats = (size_t)rows_pad * W * 3;
+            rc = grow(ctx, &d0.d_gather, &d0.gather_cap, tile_floats * G);
+            if (rc) return rc;
+            for (int g = 0; g < G; ++g) {
+                DeviceState& ds = ctx->dev[g];
+                RTW_CUDA(ctx, cudaSetDevice(ds.device));
+                float* dst = d0.d_gather + tile_floats * g;
+                float* tile = dst;
+                if (g != 0) {
+                    rc = grow(ctx, &ds.d_tile, &ds.tile_cap, tile_floats);
+                    if (rc) return rc;
+                    tile = ds.d_tile;
+                }
+                rc = enqueue_resolve(ctx, ds, W, g, G, 0, divisor, ps.s_total, tile, ds.stream, timing);
+                if (rc) return rc;
+                if (g != 0) {
+                    // framebuffer gather: tile -> device 0 over NVLink (peer copy on the producer's stream)
+                    size_t bytes = (size_t)rows_of(H, g, G) * W * 3 * sizeof(float);
+                    if (bytes) RTW_CUDA(ctx, cudaMemcpyPeerAsync(dst, d0.device, tile, ds.device, bytes, ds.stream));
+                    RTW_CUDA(ctx, cudaEventRecord(ds.ev_tile, ds.stream));
+                }
+            }
+            RTW_CUDA(ctx, cudaSetDevice(d0.device));
+            for (int g = 1; g < G; ++g) RTW_CUDA(ctx, cudaStreamWaitEvent(d0.stream, ctx->dev[g].ev_tile, 0));
+            RTW_CUDA(ctx, rtw::launch_assemble(d0.d_gather, G, W, H, d0.d_image, d0.stream));
+        }
+    }
+    RTW_CUDA(ctx, cudaSetDevice(d0.device));
     RTW_CUDA(ctx, cudaEventRecord(d0.ev[4], d0.stream));
-    if (img_floats)
-        RTW_CUDA(ctx, cudaMemcpyAsync(out_rgb, d0.d_image, img_floats * sizeof(float), cudaMemcpyDeviceToHost, d0.stream));
+    int extra_launches = (do_resolve && G > 1) ? 1 : 0;
+    if (do_resolve && img_floats) {
+        if (out_rgb)
+            RTW_CUDA(ctx, cudaMemcpyAsync(out_rgb, d0.d_image, img_floats * sizeof(float), cudaMemcpyDeviceToHost, d0.stream));
+        if (out_rgb8) {
+            // 8-bit image: reuse the gather buffer as scratch (W*H*3 bytes <= its size is not guaranteed: own buffer)
+            rc = grow(ctx, &d0.d_rgb8, &d0.rgb8_cap, img_floats);
+            if (rc) return rc;
+            RTW_CUDA(ctx, rtw::launch_quantize_rgb8(d0.d_image, W, H, d0.d_rgb8, d0.stream));
+            extra_launches += 1;
+            RTW_CUDA(ctx, cudaMemcpyAsync(out_rgb8, d0.d_rgb8, img_floats, cudaMemcpyDeviceToHost, d0.stream));
+        }
+    }
     RTW_CUDA(ctx, cudaEventRecord(d0.ev[5], d0.stream));
     for (int g = G - 1; g >= 0; --g) {
         RTW_CUDA(ctx, cudaSetDevice(ctx->dev[g].device));
@@ -412,8 +490,10 @@ int render_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int spp, int max_d
     for (int g = 0; g < G; ++g) {
         DeviceState& ds = ctx->dev[g];
         RTW_CUDA(ctx, cudaSetDevice(ds.device));
-        rc = finish_stats(ctx, ds, timing);
-        if (rc) return rc;
+        if (do_trace) {
+            rc = finish_stats(ctx, ds, timing);
+            if (rc) return rc;
+        }
         total.paths += ds.last.paths;
         total.ray_segments += ds.last.ray_segments;
         total.sphere_tests += ds.last.sphere_tests;
@@ -422,7 +502,7 @@ int render_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int spp, int max_d
         total.ms_trace = std::fmax(total.ms_trace, ds.last.ms_trace);
         total.ms_resolve = std::fmax(total.ms_resolve, ds.last.ms_resolve);
     }
-    if (G > 1) total.kernel_launches += 1;
+    total.kernel_launches += extra_launches;
     RTW_CUDA(ctx, cudaSetDevice(d0.device));
     float ms = 0.f;
     RTW_CUDA(ctx, cudaEventElapsedTime(&ms, d0.ev[3], d0.ev[5]));
@@ -433,6 +513,16 @@ int render_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int spp, int max_d
     total.ms_h2d = ms;
     if (stats) *stats = total;
     return RTW_OK;
+}
+
+int render_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int spp, int max_depth, uint64_t seed, float* out_rgb,
+                  rtw_stats* stats, bool scene_uploaded_in_call) {
+    int rc = check_render_args(ctx, cam, W, spp, max_depth);
+    if (rc) return rc;
+    if (!out_rgb) return fail(ctx, RTW_E_INVALID_ARG, "out_rgb is NULL");
+    ctx->prog = ProgressiveState{};  // a plain render() owns the accumulators: any progressive image is gone
+    return pass_locked(ctx, cam, W, max_depth, seed, PassSpec{0, spp, spp, true}, true, true, spp, out_rgb, nullptr, stats,
+                       scene_uploaded_in_call);
 }
 
 }  // namespace
@@ -520,7 +610,7 @@ int rtw_destroy(rtw_ctx* ctx) {
         cudaFree(ds.d_geom); cudaFree(ds.d_geom_pairs); cudaFree(ds.d_mat); cudaFree(ds.d_kind);
         cudaFree(ds.d_geom_perm[0]); cudaFree(ds.d_geom_perm[1]); cudaFree(ds.d_uv);
         cudaFree(ds.d_accum); cudaFree(ds.d_counters); cudaFree(ds.d_tile);
-        cudaFree(ds.d_gather); cudaFree(ds.d_image); cudaFree(ds.d_scratch); cudaFree(ds.d_wf);
+        cudaFree(ds.d_gather); cudaFree(ds.d_image); cudaFree(ds.d_rgb8); cudaFree(ds.d_scratch); cudaFree(ds.d_wf);
         if (ds.h_counters) cudaFreeHost(ds.h_counters);
         for (auto& e : ds.ev) if (e) cudaEventDestroy(e);
         if (ds.ev_tile) cudaEventDestroy(ds.ev_tile);
@@ -632,6 +722,7 @@ int rtw_render_rows_device(rtw_ctx* ctx, int device_slot, const rtw_camera* cam,
             return fail(ctx, RTW_E_INVALID_ARG, "column_major output needs row_start=0,row_stride=1");
         DeviceState& ds = ctx->dev[device_slot];
         cudaStream_t s = stream ? (cudaStream_t)stream : ds.stream;
+        ctx->prog = ProgressiveState{};  // this device's accumulator is reused
         return enqueue_rows(ctx, ds, cam, image_width, n_samples, max_depth, seed, row_start, row_stride, column_major,
                             d_tile, s, ctx->collect_timing != 0);
     } catch (...) {
@@ -664,6 +755,130 @@ int rtw_assemble_tiles_device(rtw_ctx* ctx, int device_slot, const float* d_tile
     cudaStream_t s = stream ? (cudaStream_t)stream : ds.stream;
     RTW_CUDA(ctx, rtw::launch_assemble(d_tiles, n_tiles, image_width, rtw_image_height(image_width), d_out_rgb, s));
     return RTW_OK;
+}
+
+int rtw_accumulate(rtw_ctx* ctx, const rtw_camera* cam, int image_width, int sample_first, int sample_count,
+                   int n_samples_total, int max_depth, uint64_t seed, rtw_stats* stats) {
+    if (!ctx) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    try {
+        int rc = check_render_args(ctx, cam, image_width, n_samples_total, max_depth);
+        if (rc) return rc;
+        if (sample_first < 0 || sample_count < 1 || sample_first > n_samples_total - sample_count)
+            return fail(ctx, RTW_E_INVALID_ARG, "samples must satisfy 0 <= first, 1 <= count, first + count <= total");
+        ProgressiveState& pg = ctx->prog;
+        if (sample_first != 0) {
+            if (!pg.valid || pg.W != image_width || pg.s_total != n_samples_total || pg.s_done != sample_first)
+                return fail(ctx, RTW_E_INVALID_ARG, "sample_first must continue the progressive image held by the context "
+                                                    "(same width and total, first == samples accumulated so far)");
+        }
+        const PassSpec ps{sample_first, sample_count, n_samples_total, sample_first == 0};
+        pg.valid = false;  // stays invalid if the pass fails half-way
+        rc = pass_locked(ctx, cam, image_width, max_depth, seed, ps, true, false, 0, nullptr, nullptr, stats, false);
+        if (rc) return rc;
+        pg.valid = true;
+        pg.W = image_width;
+        pg.s_total = n_samples_total;
+        pg.s_done = sample_first + sample_count;
+        return RTW_OK;
+    } catch (...) {
+        return fail(ctx, RTW_E_INTERNAL, "unexpected C++ exception in rtw_accumulate");
+    }
+}
+
+static int resolve_common(rtw_ctx* ctx, float* out_rgb, uint8_t* out_rgb8) {
+    if (!ctx) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    try {
+        if (!out_rgb && !out_rgb8) return fail(ctx, RTW_E_INVALID_ARG, "output buffer is NULL");
+        const ProgressiveState& pg = ctx->prog;
+        if (!pg.valid || pg.s_done < 1) return fail(ctx, RTW_E_INVALID_ARG, "no progressive image: call rtw_accumulate first");
+        const PassSpec ps{0, 0, pg.s_total, false};
+        return pass_locked(ctx, nullptr, pg.W, 0, 0, ps, false, true, pg.s_done, out_rgb, out_rgb8, nullptr, false);
+    } catch (...) {
+        return fail(ctx, RTW_E_INTERNAL, "unexpected C++ exception in rtw_resolve");
+    }
+}
+
+int rtw_resolve(rtw_ctx* ctx, float* out_rgb) { return resolve_common(ctx, out_rgb, nullptr); }
+
+int rtw_resolve_rgb8(rtw_ctx* ctx, uint8_t* out_rgb8) { return resolve_common(ctx, nullptr, out_rgb8); }
+
+int rtw_progress(rtw_ctx* ctx, int* image_width, int* samples_done, int* samples_total) {
+    if (!ctx) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const ProgressiveState& pg = ctx->prog;
+    if (image_width) *image_width = pg.valid ? pg.W : 0;
+    if (samples_done) *samples_done = pg.valid ? pg.s_done : 0;
+    if (samples_total) *samples_total = pg.valid ? pg.s_total : 0;
+    return RTW_OK;
+}
+
+// rows r = g, g + G, ... of the image live, compacted, in device g's accumulator
+static int accumulator_copy(rtw_ctx* ctx, int W, int64_t* host_out, const int64_t* host_in) {
+    const int H = rtw_image_height(W);
+    const int G = (int)ctx->dev.size();
+    std::vector<int64_t> tmp;
+    for (int g = 0; g < G; ++g) {
+        DeviceState& ds = ctx->dev[g];
+        const int n_rows = rows_of(H, g, G);
+        const size_t vals = (size_t)n_rows * (size_t)W * 4;
+        if (vals == 0) continue;
+        RTW_CUDA(ctx, cudaSetDevice(ds.device));
+        tmp.resize(vals);
+        if (host_in) {
+            for (int k = 0; k < n_rows; ++k)
+                std::memcpy(tmp.data() + (size_t)k * W * 4, host_in + (size_t)(g + k * G) * W * 4, (size_t)W * 4 * sizeof(int64_t));
+            int rc = grow(ctx, &ds.d_accum, &ds.accum_cap, vals);
+            if (rc) return rc;
+            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_accum, tmp.data(), vals * sizeof(int64_t), cudaMemcpyHostToDevice, ds.stream));
+            RTW_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+        } else {
+            if (vals > ds.accum_cap) return fail(ctx, RTW_E_INTERNAL, "accumulator smaller than the progressive image");
+            RTW_CUDA(ctx, cudaMemcpyAsync(tmp.data(), ds.d_accum, vals * sizeof(int64_t), cudaMemcpyDeviceToHost, ds.stream));
+            RTW_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+            for (int k = 0; k < n_rows; ++k)
+                std::memcpy(host_out + (size_t)(g + k * G) * W * 4, tmp.data() + (size_t)k * W * 4, (size_t)W * 4 * sizeof(int64_t));
+        }
+    }
+    return RTW_OK;
+}
+
+int rtw_accumulator_read(rtw_ctx* ctx, int64_t* out, uint64_t n_values) {
+    if (!ctx) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    try {
+        const ProgressiveState& pg = ctx->prog;
+        if (!pg.valid) return fail(ctx, RTW_E_INVALID_ARG, "no progressive image: call rtw_accumulate first");
+        const uint64_t need = (uint64_t)pg.W * (uint64_t)rtw_image_height(pg.W) * 4ull;
+        if (!out || n_values != need) return fail(ctx, RTW_E_INVALID_ARG, "out must hold H*W*4 int64 values");
+        return accumulator_copy(ctx, pg.W, out, nullptr);
+    } catch (...) {
+        return fail(ctx, RTW_E_INTERNAL, "unexpected C++ exception in rtw_accumulator_read");
+    }
+}
+
+int rtw_accumulator_write(rtw_ctx* ctx, const int64_t* in, uint64_t n_values, int image_width, int samples_done,
+                          int samples_total) {
+    if (!ctx) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    try {
+        if (image_width < 1 || image_width > 65536 || samples_total < 1 || samples_total > (1 << 24) || samples_done < 0 ||
+            samples_done > samples_total)
+            return fail(ctx, RTW_E_INVALID_ARG, "bad image_width / samples_done / samples_total");
+        const uint64_t need = (uint64_t)image_width * (uint64_t)rtw_image_height(image_width) * 4ull;
+        if (!in || n_values != need) return fail(ctx, RTW_E_INVALID_ARG, "in must hold H*W*4 int64 values");
+        ctx->prog = ProgressiveState{};
+        int rc = accumulator_copy(ctx, image_width, nullptr, in);
+        if (rc) return rc;
+        ctx->prog.valid = true;
+        ctx->prog.W = image_width;
+        ctx->prog.s_total = samples_total;
+        ctx->prog.s_done = samples_done;
+        return RTW_OK;
+    } catch (...) {
+        return fail(ctx, RTW_E_INTERNAL, "unexpected C++ exception in rtw_accumulator_write");
+    }
 }
 
 int rtw_measure_fp32_peak(rtw_ctx* ctx, int device_slot, int variant, double* fp32_instr_per_s, float* ms_out) {

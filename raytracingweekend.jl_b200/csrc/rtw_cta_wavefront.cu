@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(kCtaBlock, 3) cta_wavefront_kernel(const __gri
                             pl = (uint32_t)q;
                             s0 = (uint32_t)(ticket - q * (unsigned)P.spp);
                         }
+                        s0 += (uint32_t)P.sample_first;
                         const uint32_t row_local = pl / (uint32_t)P.W, col = pl - row_local * (uint32_t)P.W;
                         const uint32_t i0 = (uint32_t)P.row_start + row_local * (uint32_t)P.row_stride;
                         const float su = __fdiv_rn((float)(col + 1u), (float)P.W);                  // src/render.jl:26

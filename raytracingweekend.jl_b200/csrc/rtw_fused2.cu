@@ -478,6 +478,7 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
                 pl = (uint32_t)q;
                 s0 = (uint32_t)(ticket - q * (unsigned)P.spp);
             }
+            s0 += (uint32_t)P.sample_first;
             const uint32_t row_local = magic_div(pl, P.div_w);
             const uint32_t col = pl - row_local * (uint32_t)P.W;
             const uint32_t i0 = (uint32_t)P.row_start + row_local * (uint32_t)P.row_stride;

@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
                     pl = (uint32_t)q;
                     s0 = (uint32_t)(ticket - q * (unsigned)P.spp);
                 }
+                s0 += (uint32_t)P.sample_first;
                 uint32_t row_local = pl / (uint32_t)P.W;
                 uint32_t col = pl - row_local * (uint32_t)P.W;
                 uint32_t i0 = (uint32_t)P.row_start + row_local * (uint32_t)P.row_stride;

@@ -33,7 +33,8 @@ struct TraceParams {
     const float4* mat;
     const uint32_t* kind;
     uint32_t n_spheres;
-    int W, H, spp, max_depth;
+    int W, H, spp, max_depth;  // spp = samples per pixel traced by THIS launch
+    int sample_first;          // they are samples sample_first .. sample_first + spp - 1 of the image (progressive passes)
     uint32_t key0, key1;  // Philox key = seed lo/hi
     int row_start, row_stride, n_rows;
     unsigned long long n_paths;  // n_rows * W * spp ; path ticket t -> pixel t / spp, sample t % spp
@@ -89,6 +90,8 @@ cudaError_t launch_cta_wavefront_trace(const TraceParams& p, int num_sms, int bl
 cudaError_t launch_resolve(const unsigned long long* accum, int W, int H, int n_rows, int row_start, int row_stride,
                            int spp, double inv_scale, int column_major, float* out, cudaStream_t stream);
 cudaError_t launch_assemble(const float* tiles, int n_tiles, int W, int H, float* out, cudaStream_t stream);
+// Julia column-major Float32 image -> row-major 8-bit RGB, clamp01nan + N0f8 rounding (rtw_image.cu)
+cudaError_t launch_quantize_rgb8(const float* img, int W, int H, unsigned char* out, cudaStream_t stream);
 // FP32 issue microbenchmarks; returns lane-instructions executed through *fp32_instr
 cudaError_t launch_fp32_peak(int variant, int num_sms, float* scratch, cudaStream_t stream, double* fp32_instr);
 

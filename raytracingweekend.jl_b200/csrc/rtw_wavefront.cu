@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kWfBlock) wf_terminate_regenerate_kernel(const
             continue;
         }
         const unsigned long long q = ticket / (unsigned)P.spp;
-        const uint32_t pl = (uint32_t)q, s0 = (uint32_t)(ticket - q * (unsigned)P.spp);
+        const uint32_t pl = (uint32_t)q, s0 = (uint32_t)(ticket - q * (unsigned)P.spp) + (uint32_t)P.sample_first;
         const uint32_t row_local = pl / (uint32_t)P.W, col = pl - row_local * (uint32_t)P.W;
         const uint32_t i0 = (uint32_t)P.row_start + row_local * (uint32_t)P.row_stride;
         const float su = __fdiv_rn((float)(col + 1u), (float)P.W);                       // src/render.jl:26

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(rtw):
 
 def test_abi_version_and_image_height(rtw):
     lib = rtw._lib.load()
-    assert lib.rtw_abi_version() == 1
+    assert lib.rtw_abi_version() == 2
     for w, h in [(96, 54), (400, 225), (1920, 1080), (200, 112), (1, 0)]:
         assert lib.rtw_image_height(w) == h
 

@@ -385,3 +385,64 @@ def test_high_seed_bits_and_many_samples(rtw, oracle, renderer, scenes):
     other = renderer.render(cam, 32, 8, max_depth=8, seed=seed ^ (1 << 40), scene=scenes["four"])
     base = renderer.render(cam, 32, 8, max_depth=8, seed=seed, scene=scenes["four"])
     assert not np.array_equal(np.array(other), np.array(base))  # the high key word matters
+
+
+def test_progressive_passes_checkpoint_and_rgb8(rtw, oracle, renderer, scenes, tmp_path):
+    # render() split into passes over the samples is bit-identical to one render (addressed stream + integer
+    # accumulator); the accumulators can be saved and installed into another context; 8-bit output = clamp01nan + N0f8
+    cam, W, total, depth, seed = rtw.t_cam1(), 160, 24, 16, 9
+    renderer.set_scene(scenes["random"])
+    full = np.array(renderer.render(cam, W, total, max_depth=depth, seed=seed))
+    segs_full = renderer.last_stats["ray_segments"]
+    ref, _, ost = oracle.render(*scenes["random"], cam.as_array(), W, total, max_depth=depth, seed=seed)
+    _compare(full, ref)
+    assert renderer.progress() == (0, 0, 0)
+    segs = 0
+    for first, count in [(0, 5), (5, 1)]:
+        segs += renderer.accumulate(cam, W, first, count, total, max_depth=depth, seed=seed)["ray_segments"]
+    assert renderer.progress() == (W, 6, total)
+    preview = np.array(renderer.resolve())  # 6 of 24 samples: equals a 6-spp render up to the fixed-point quantum
+    ref6, _, _ = oracle.render(*scenes["random"], cam.as_array(), W, 6, max_depth=depth, seed=seed)
+    assert np.abs(preview.astype(np.float64) - ref6).max() < 1e-6
+    checkpoint = renderer.accumulator_read()
+    assert checkpoint.shape == (90, W, 4) and checkpoint.dtype == np.int64 and (checkpoint[..., :3] >= 0).all()
+    segs += renderer.accumulate(cam, W, 6, 18, total, max_depth=depth, seed=seed)["ray_segments"]
+    img = np.array(renderer.resolve())
+    assert np.array_equal(img, full) and segs == segs_full == ost["ray_segments"]
+    # 8-bit image and files
+    u8 = renderer.resolve_rgb8()
+    expect = np.rint(np.clip(full, 0.0, 1.0).astype(np.float32) * np.float32(255.0)).astype(np.uint8)
+    assert u8.shape == (90, W, 3) and np.array_equal(u8, expect)
+    rtw.write_png(tmp_path / "img.png", u8)
+    rtw.write_ppm(tmp_path / "img.ppm", u8)
+    assert (tmp_path / "img.png").stat().st_size > u8.size and (tmp_path / "img.ppm").stat().st_size == u8.size + 14
+    # resume in a fresh context from the checkpoint
+    with rtw.Renderer([0]) as r2:
+        r2.set_scene(scenes["random"])
+        r2.accumulator_write(checkpoint, W, 6, total)
+        r2.accumulate(cam, W, 6, 18, total, max_depth=depth, seed=seed)
+        assert np.array_equal(np.array(r2.resolve()), full)
+    # misuse: gaps, wrong total, nothing accumulated
+    for args in [(W, 20, 4, total), (W, 24, 1, total), (W, 6, 1, total + 1), (W + 16, 24, 0, total)]:
+        with pytest.raises(rtw.RtwError) as e:
+            renderer.accumulate(cam, args[0], args[1], args[2], args[3], max_depth=depth, seed=seed)
+        assert e.value.code == rtw._lib.RTW_E_INVALID_ARG
+    renderer.render(cam, 64, 1)  # a plain render discards the progressive image
+    with pytest.raises(rtw.RtwError):
+        renderer.resolve()
+
+
+@pytest.mark.parametrize("mode,tail", [(0, 1), (0, 2), (1, 0), (2, 0)])
+def test_progressive_passes_in_every_mode(rtw, renderer, scenes, mode, tail):
+    cam = rtw.t_default_cam()
+    renderer.set_scene(scenes["bubble"])
+    renderer.set_option(rtw.RTW_OPT_MODE, mode)
+    renderer.set_option(rtw.RTW_OPT_TAIL, tail)
+    try:
+        full = np.array(renderer.render(cam, 96, 12, max_depth=20, seed=4))
+        renderer.accumulate(cam, 96, 0, 7, 12, max_depth=20, seed=4)
+        renderer.accumulate(cam, 96, 7, 5, 12, max_depth=20, seed=4)
+        assert np.array_equal(np.array(renderer.resolve()), full)
+    finally:
+        renderer.set_option(rtw.RTW_OPT_MODE, 0)
+        renderer.set_option(rtw.RTW_OPT_TAIL, 0)

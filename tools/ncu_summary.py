@@ -10,6 +10,23 @@ import sys
 from collections import Counter
 
 
+import re
+
+# the metrics the summaries under profiles/ quote (the full set stays in the .ncu-rep under gpurun_out/)
+KEEP = re.compile(r"^(Kernel Name|Block Size|Grid Size|launch__(registers_per_thread|shared_mem_per_block_(dynamic|static)|"
+                  r"occupancy_limit_\w+|waves_per_multiprocessor)|gpu__time_duration\.sum|dram__bytes_(read|write)\.sum|"
+                  r"dram__throughput\.avg\.pct_of_peak_sustained_elapsed|lts__t_bytes\.sum|lts__t_sector_hit_rate\.pct|"
+                  r"l1tex__m_xbar2l1tex_read_bytes\.sum|l1tex__data_bank_conflicts_pipe_lsu\.sum|"
+                  r"l1tex__data_pipe_lsu_wavefronts_mem_shared\.sum|sm__throughput\.avg\.pct_of_peak_sustained_elapsed|"
+                  r"sm__pipe_(fma|fmaheavy|fmalite|alu|fp64|xu)_cycles_active\.avg\.pct_of_peak_sustained_active|"
+                  r"sm__inst_executed_pipe_(fma|alu|lsu|xu|fp64|uniform|cbu|adu)\.sum\.pct_of_peak_sustained_active|"
+                  r"sm__inst_executed_pipe_\w+\.sum|smsp__inst_executed\.sum|smsp__issue_active\.avg\.pct_of_peak_sustained_active|"
+                  r"smsp__warps_eligible\.avg\.per_cycle_active|sm__warps_active\.avg\.pct_of_peak_sustained_active|"
+                  r"smsp__thread_inst_executed_per_inst_executed\.ratio|"
+                  r"smsp__average_warps_issue_stalled_\w+_per_issue_active\.ratio|sm__cycles_elapsed\.avg|"
+                  r"sm__cycles_active\.avg|smsp__cycles_active\.avg)$")
+
+
 def ncu_csv(rep, page):
     out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
@@ -22,7 +39,7 @@ def main():
     with open(out + "_full_metrics.csv", "w") as f:
         f.write("metric,unit,value\n")
         for h, u, v in zip(hdr, units, vals):
-            if h in ("ID", "Process ID", "Process Name", "Host Name", "Context", "Stream", "Device", "CC"):
+            if not KEEP.search(h):
                 continue
             f.write(f"{h},{u},{v}\n".replace("rtw::<", "<"))
     rows = ncu_csv(rep, "source")

@@ -14,6 +14,7 @@ module RayTracingWeekendB200
 using RayTracingWeekend
 using RayTracingWeekend: Camera, HittableList, Sphere, Lambertian, Metal, Dielectric
 using Images: RGB
+using StaticArrays: SA
 
 const librtw = get(ENV, "RTW_B200_LIB", joinpath(@__DIR__, "..", "csrc", "librtw_b200.so"))
 
@@ -118,11 +119,81 @@ end
 render_b200(scene::HittableList, cam::Camera, args...; kw...) =
     error("rtw_b200: only Camera{Float32} is supported on the CUDA path (there is no CPU fallback)")
 
+# ---- progressive rendering, image and scene files (C-ABI v2) ----------------------------------------------------
+# render() split into passes over the samples: every draw is addressed by (pixel, sample, event) and the accumulator
+# is an integer sum, so accumulate!(…, 0, a, n) + accumulate!(…, a, n - a, n) gives the bits of render(…, n).
+
+set_scene!(ctx::Context, scene::HittableList) = begin
+    geom, mat, kind = flatten(scene)
+    GC.@preserve geom mat kind check(ctx.ptr, ccall((:rtw_set_scene, librtw), Cint,
+        (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt32}, UInt32), ctx.ptr, geom, mat, kind, length(kind)))
+end
+
+"adds samples `first .. first+count-1` (0-based) of every pixel; `first == 0` starts a new image of `total` samples"
+function accumulate!(ctx::Context, cam::Camera{Float32}, image_width::Integer, first::Integer, count::Integer,
+                     total::Integer; max_depth::Integer = 16, seed::Integer = 1)
+    st = Ref{RtwStats}()
+    camref = Ref(cam)
+    GC.@preserve camref check(ctx.ptr, ccall((:rtw_accumulate, librtw), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, UInt64, Ptr{RtwStats}),
+        ctx.ptr, camref, image_width, first, count, total, max_depth, seed, st))
+    st[]
+end
+
+"the image of the samples accumulated so far, as `render` returns it"
+function resolve(ctx::Context)
+    w, done, total = Ref{Cint}(0), Ref{Cint}(0), Ref{Cint}(0)
+    check(ctx.ptr, ccall((:rtw_progress, librtw), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), ctx.ptr, w, done, total))
+    H = Int(ccall((:rtw_image_height, librtw), Cint, (Cint,), w[]))
+    img = Matrix{RGB{Float32}}(undef, H, Int(w[]))
+    GC.@preserve img check(ctx.ptr, ccall((:rtw_resolve, librtw), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.ptr, img))
+    img
+end
+
+"`save(path, img)` without Images.jl's writers: 8-bit PNG of the progressive image (clamp01nan + N0f8 rounding)"
+function save_png(ctx::Context, path::AbstractString)
+    w, done, total = Ref{Cint}(0), Ref{Cint}(0), Ref{Cint}(0)
+    check(ctx.ptr, ccall((:rtw_progress, librtw), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), ctx.ptr, w, done, total))
+    H = Int(ccall((:rtw_image_height, librtw), Cint, (Cint,), w[]))
+    rgb8 = Vector{UInt8}(undef, 3 * H * Int(w[]))     # row-major, top row first
+    GC.@preserve rgb8 begin
+        check(ctx.ptr, ccall((:rtw_resolve_rgb8, librtw), Cint, (Ptr{Cvoid}, Ptr{UInt8}), ctx.ptr, rgb8))
+        check(C_NULL, ccall((:rtw_write_png, librtw), Cint, (Cstring, Ptr{UInt8}, Cint, Cint), path, rgb8, w[], H))
+    end
+    path
+end
+
+"writes the flattened HittableList as a `.rtwscene` file (the fixture format shared with the Python harness / oracle)"
+function save_scene(path::AbstractString, scene::HittableList)
+    geom, mat, kind = flatten(scene)
+    GC.@preserve geom mat kind check(C_NULL, ccall((:rtw_scene_save, librtw), Cint,
+        (Cstring, Ptr{Float32}, Ptr{Float32}, Ptr{UInt32}, UInt32), path, geom, mat, kind, length(kind)))
+    path
+end
+
+"reads a `.rtwscene` file back into a HittableList of Float32 spheres"
+function load_scene(path::AbstractString)
+    n = Ref{UInt32}(0)
+    check(C_NULL, ccall((:rtw_scene_load, librtw), Cint,
+        (Cstring, Ptr{Float32}, Ptr{Float32}, Ptr{UInt32}, UInt32, Ptr{UInt32}), path, C_NULL, C_NULL, C_NULL, 0, n))
+    geom, mat, kind = Matrix{Float32}(undef, 4, n[]), Matrix{Float32}(undef, 4, n[]), Vector{UInt32}(undef, n[])
+    GC.@preserve geom mat kind check(C_NULL, ccall((:rtw_scene_load, librtw), Cint,
+        (Cstring, Ptr{Float32}, Ptr{Float32}, Ptr{UInt32}, UInt32, Ptr{UInt32}), path, geom, mat, kind, n[], n))
+    scene = HittableList()
+    for k in 1:Int(n[])
+        albedo = SA[mat[1, k], mat[2, k], mat[3, k]]
+        m = kind[k] == RTW_LAMBERTIAN ? Lambertian(albedo) :
+            kind[k] == RTW_METAL ? Metal(albedo, mat[4, k]) : Dielectric(mat[4, k])
+        push!(scene, Sphere(SA[geom[1, k], geom[2, k], geom[3, k]], geom[4, k], m))
+    end
+    scene
+end
+
 # To make it a true drop-in, overload the reference's method for Float32 cameras:
 #     import RayTracingWeekend: render
 #     render(scene::HittableList, cam::Camera{Float32}, image_width=400, n_samples=1) =
 #         RayTracingWeekendB200.render_b200(scene, cam, image_width, n_samples)
 
-export render_b200, Context, RtwStats
+export render_b200, Context, RtwStats, set_scene!, accumulate!, resolve, save_png, save_scene, load_scene
 
 end # module

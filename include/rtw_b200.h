@@ -196,6 +196,33 @@ RTW_API int rtw_last_stats(rtw_ctx* ctx, int device_slot, rtw_stats* stats);
 RTW_API int rtw_assemble_tiles_device(rtw_ctx* ctx, int device_slot, const float* d_tiles, int n_tiles, int image_width,
                               float* d_out_rgb, void* stream);
 
+/* ---- Float64 (the reference is generic over T; its own test and published timings use Float64) ----------- */
+
+/* Camera{Float64}: same field order as rtw_camera, 22 doubles (src/camera.jl:1-10) */
+typedef struct rtw_camera_f64 {
+    double origin[3];
+    double lower_left_corner[3];
+    double horizontal[3];
+    double vertical[3];
+    double u[3];
+    double v[3];
+    double w[3];
+    double lens_radius;
+} rtw_camera_f64;
+
+/*
+ * The Float64 instantiation of rtw_set_scene / rtw_render / rtw_render_scene: scene arrays and image are doubles
+ * (out_rgb = memory of Matrix{RGB{Float64}}(H, W)), the path is traced in Float64 on the FP64 pipe with the same
+ * addressed stream (a Float64 draw takes two words: 52 random mantissa bits).  The Float64 scene is held separately
+ * from the Float32 one.
+ */
+RTW_API int rtw_set_scene_f64(rtw_ctx* ctx, const double* geom4, const double* mat4, const uint32_t* kind, uint32_t n_spheres);
+RTW_API int rtw_render_f64(rtw_ctx* ctx, const rtw_camera_f64* cam, int image_width, int n_samples, int max_depth,
+                           uint64_t seed, double* out_rgb, rtw_stats* stats);
+RTW_API int rtw_render_scene_f64(rtw_ctx* ctx, const double* geom4, const double* mat4, const uint32_t* kind,
+                                 uint32_t n_spheres, const rtw_camera_f64* cam, int image_width, int n_samples,
+                                 int max_depth, uint64_t seed, double* out_rgb, rtw_stats* stats);
+
 /* ---- progressive rendering ------------------------------------------------------------------- */
 
 /*

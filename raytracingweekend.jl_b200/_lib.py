@@ -28,6 +28,9 @@ EXPORTED_SYMBOLS = (
     "rtw_last_stats",
     "rtw_assemble_tiles_device",
     "rtw_measure_fp32_peak",
+    "rtw_set_scene_f64",
+    "rtw_render_f64",
+    "rtw_render_scene_f64",
     "rtw_accumulate",
     "rtw_resolve",
     "rtw_resolve_rgb8",
@@ -101,6 +104,21 @@ class rtw_camera(C.Structure):
     ]
 
 
+class rtw_camera_f64(C.Structure):
+    """Camera{Float64}: the same 22 fields as doubles."""
+
+    _fields_ = [
+        ("origin", C.c_double * 3),
+        ("lower_left_corner", C.c_double * 3),
+        ("horizontal", C.c_double * 3),
+        ("vertical", C.c_double * 3),
+        ("u", C.c_double * 3),
+        ("v", C.c_double * 3),
+        ("w", C.c_double * 3),
+        ("lens_radius", C.c_double),
+    ]
+
+
 class rtw_stats(C.Structure):
     _fields_ = [
         ("paths", C.c_uint64),
@@ -169,6 +187,14 @@ def load() -> C.CDLL:
     lib.rtw_assemble_tiles_device.argtypes = [vp, i32, vp, i32, i32, vp, vp]
     lib.rtw_measure_fp32_peak.restype = i32
     lib.rtw_measure_fp32_peak.argtypes = [vp, i32, i32, C.POINTER(C.c_double), fp]
+    dp = C.POINTER(C.c_double)
+    lib.rtw_set_scene_f64.restype = i32
+    lib.rtw_set_scene_f64.argtypes = [vp, dp, dp, u32p, u32]
+    lib.rtw_render_f64.restype = i32
+    lib.rtw_render_f64.argtypes = [vp, C.POINTER(rtw_camera_f64), i32, i32, i32, u64, dp, C.POINTER(rtw_stats)]
+    lib.rtw_render_scene_f64.restype = i32
+    lib.rtw_render_scene_f64.argtypes = [vp, dp, dp, u32p, u32, C.POINTER(rtw_camera_f64), i32, i32, i32, u64, dp,
+                                         C.POINTER(rtw_stats)]
     u8p, i64p, i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int64), C.POINTER(i32)
     lib.rtw_accumulate.restype = i32
     lib.rtw_accumulate.argtypes = [vp, C.POINTER(rtw_camera), i32, i32, i32, i32, i32, u64, C.POINTER(rtw_stats)]

@@ -12,8 +12,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import RtwError, rtw_camera, rtw_stats
-from .host import Camera, F32, Sphere, flatten_scene, image_height
+from ._lib import RtwError, rtw_camera, rtw_camera_f64, rtw_stats
+from .host import Camera, F32, F64, Sphere, flatten_scene, image_height
 
 DEFAULT_MAX_DEPTH = 16  # ray_color's default depth, src/ray_color.jl:14
 DEFAULT_SEED = 1        # reseed!() semantics: the same image on every call, src/render.jl:21
@@ -21,13 +21,25 @@ DEFAULT_SEED = 1        # reseed!() semantics: the same image on every call, src
 
 def _camera_struct(cam: Camera) -> rtw_camera:
     if cam.elem_type != F32:
-        raise RtwError(_lib.RTW_E_UNSUPPORTED, "only Camera{Float32} is supported on the CUDA path (no CPU fallback)")
+        raise RtwError(_lib.RTW_E_UNSUPPORTED, "this entry point takes a Camera{Float32} (render() also serves Camera{Float64})")
     c = rtw_camera()
     for name in ("origin", "lower_left_corner", "horizontal", "vertical", "u", "v", "w"):
         arr = np.asarray(getattr(cam, name), dtype=F32)
         getattr(c, name)[:] = [float(x) for x in arr]
     c.lens_radius = float(cam.lens_radius)
     return c
+
+
+def _camera_struct_f64(cam: Camera) -> rtw_camera_f64:
+    c = rtw_camera_f64()
+    for name in ("origin", "lower_left_corner", "horizontal", "vertical", "u", "v", "w"):
+        getattr(c, name)[:] = [float(x) for x in np.asarray(getattr(cam, name), dtype=F64)]
+    c.lens_radius = float(cam.lens_radius)
+    return c
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
 def _fp(a: np.ndarray):
@@ -90,6 +102,8 @@ class Renderer:
         (rtw_render_scene)."""
         W = int(image_width)
         H = image_height(W)
+        if cam.elem_type == F64:
+            return self._render_f64(cam, W, H, int(n_samples), int(max_depth), int(seed), scene, out)
         if out is None:
             out = np.empty((W, H, 3), dtype=F32)  # C-order (W,H,3) == column-major H x W of RGB
         elif out.shape != (W, H, 3) or out.dtype != F32 or not out.flags.c_contiguous:
@@ -106,6 +120,29 @@ class Renderer:
         else:
             status = self._lib.rtw_render(self._ctx, C.byref(cs), W, int(n_samples), int(max_depth), int(seed),
                                           _fp(out), C.byref(st))
+        self._check(status)
+        self.last_stats = st.as_dict()
+        return out.transpose(1, 0, 2)
+
+    # -- Camera{Float64}: the Float64 instantiation (scene arrays and image are doubles)
+    def set_scene_f64(self, scene) -> None:
+        geom, mat, kind = _as_flat(scene, F64)
+        self._check(self._lib.rtw_set_scene_f64(self._ctx, _dp(geom), _dp(mat), kind.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                len(kind)))
+
+    def _render_f64(self, cam, W, H, n_samples, max_depth, seed, scene, out):
+        if out is None:
+            out = np.empty((W, H, 3), dtype=F64)
+        elif out.shape != (W, H, 3) or out.dtype != F64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape (W, H, 3)")
+        cs = _camera_struct_f64(cam)
+        st = rtw_stats()
+        if scene is not None:
+            geom, mat, kind = _as_flat(scene, F64)
+            status = self._lib.rtw_render_scene_f64(self._ctx, _dp(geom), _dp(mat), kind.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                    len(kind), C.byref(cs), W, n_samples, max_depth, seed, _dp(out), C.byref(st))
+        else:
+            status = self._lib.rtw_render_f64(self._ctx, C.byref(cs), W, n_samples, max_depth, seed, _dp(out), C.byref(st))
         self._check(status)
         self.last_stats = st.as_dict()
         return out.transpose(1, 0, 2)
@@ -187,13 +224,13 @@ class Renderer:
         return rate.value, ms.value
 
 
-def _as_flat(scene):
+def _as_flat(scene, elem_type=F32):
     if isinstance(scene, tuple) and len(scene) == 3:
         geom, mat, kind = scene
     else:
-        geom, mat, kind = flatten_scene(scene)
-    geom = np.ascontiguousarray(geom, dtype=F32).reshape(-1, 4)
-    mat = np.ascontiguousarray(mat, dtype=F32).reshape(-1, 4)
+        geom, mat, kind = flatten_scene(scene, elem_type)
+    geom = np.ascontiguousarray(geom, dtype=elem_type).reshape(-1, 4)
+    mat = np.ascontiguousarray(mat, dtype=elem_type).reshape(-1, 4)
     kind = np.ascontiguousarray(kind, dtype=np.uint32).reshape(-1)
     if not (len(geom) == len(mat) == len(kind)):
         raise ValueError("geom4, mat4 and kind must have the same length")

@@ -7,7 +7,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false
        -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Xptxas -v)
-SRCS=(rtw_kernels rtw_fused2 rtw_capi rtw_image rtw_wavefront rtw_cta_wavefront)
+SRCS=(rtw_kernels rtw_fused2 rtw_f64 rtw_capi rtw_image rtw_wavefront rtw_cta_wavefront)
 pids=()
 for s in "${SRCS[@]}"; do
     "$NVCC" "${FLAGS[@]}" -c "$s.cu" -o "$s.o" > "$s.log" 2>&1 &

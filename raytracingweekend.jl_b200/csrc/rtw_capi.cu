@@ -30,6 +30,17 @@ struct DeviceState {
     float4* d_mat = nullptr;
     uint32_t* d_kind = nullptr;
     size_t scene_cap = 0;
+    // Float64 scene and image buffers (rtw_*_f64)
+    double4* d_geom64 = nullptr;
+    double4* d_mat64 = nullptr;
+    uint32_t* d_kind64 = nullptr;
+    size_t scene64_cap = 0;
+    double* d_tile64 = nullptr;
+    size_t tile64_cap = 0;
+    double* d_gather64 = nullptr;
+    size_t gather64_cap = 0;
+    double* d_image64 = nullptr;
+    size_t image64_cap = 0;
     // render buffers
     unsigned long long* d_accum = nullptr;
     size_t accum_cap = 0;  // in pixels
@@ -68,6 +79,8 @@ struct rtw_ctx {
     std::vector<DeviceState> dev;
     uint32_t n_spheres = 0;
     bool have_scene = false;
+    uint32_t n_spheres64 = 0;
+    bool have_scene64 = false;
     int mode = RTW_MODE_FUSED;
     int rays_per_lane = 0;  // 0 = default
     int sweep = 0;          // 0 = default
@@ -525,6 +538,185 @@ int render_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int spp, int max_d
                        scene_uploaded_in_call);
 }
 
+// ---- Float64 path ----------------------------------------------------------------------------------------------
+int set_scene_f64_locked(rtw_ctx* ctx, const double* geom4, const double* mat4, const uint32_t* kind, uint32_t n) {
+    if (n > 0 && (!geom4 || !mat4 || !kind)) return fail(ctx, RTW_E_INVALID_ARG, "scene arrays are NULL");
+    if (n > (1u << 26)) return fail(ctx, RTW_E_INVALID_ARG, "too many spheres");
+    for (uint32_t i = 0; i < n; ++i)
+        if (kind[i] > RTW_DIELECTRIC) return fail(ctx, RTW_E_UNSUPPORTED, "unknown material kind (only Lambertian/Metal/Dielectric)");
+    for (auto& ds : ctx->dev) {
+        RTW_CUDA(ctx, cudaSetDevice(ds.device));
+        if (n > ds.scene64_cap || !ds.d_geom64) {
+            cudaFree(ds.d_geom64); cudaFree(ds.d_mat64); cudaFree(ds.d_kind64);
+            ds.d_geom64 = nullptr; ds.d_mat64 = nullptr; ds.d_kind64 = nullptr; ds.scene64_cap = 0;
+            const size_t cap = n ? n : 1;
+            RTW_CUDA(ctx, cudaMalloc((void**)&ds.d_geom64, cap * sizeof(double4)));
+            RTW_CUDA(ctx, cudaMalloc((void**)&ds.d_mat64, cap * sizeof(double4)));
+            RTW_CUDA(ctx, cudaMalloc((void**)&ds.d_kind64, cap * sizeof(uint32_t)));
+            ds.scene64_cap = cap;
+        }
+        if (n) {
+            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_geom64, geom4, (size_t)n * 32, cudaMemcpyHostToDevice, ds.stream));
+            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_mat64, mat4, (size_t)n * 32, cudaMemcpyHostToDevice, ds.stream));
+            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_kind64, kind, (size_t)n * 4, cudaMemcpyHostToDevice, ds.stream));
+        }
+    }
+    for (auto& ds : ctx->dev) {
+        RTW_CUDA(ctx, cudaSetDevice(ds.device));
+        RTW_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+    }
+    ctx->n_spheres64 = n;
+    ctx->have_scene64 = true;
+    return RTW_OK;
+}
+
+int render_f64_locked(rtw_ctx* ctx, const rtw_camera_f64* cam, int W, int spp, int max_depth, uint64_t seed, double* out_rgb,
+                      rtw_stats* stats, bool scene_uploaded_in_call) {
+    if (!cam) return fail(ctx, RTW_E_INVALID_ARG, "camera is NULL");
+    if (W < 1 || W > 65536) return fail(ctx, RTW_E_INVALID_ARG, "image_width must be in 1..65536");
+    if (spp < 1 || spp > (1 << 24)) return fail(ctx, RTW_E_INVALID_ARG, "n_samples must be in 1..2^24");
+    if (max_depth < 0 || max_depth > (1 << 20)) return fail(ctx, RTW_E_INVALID_ARG, "max_depth must be in 0..2^20");
+    if (!ctx->have_scene64) return fail(ctx, RTW_E_NO_SCENE, "rtw_set_scene_f64 has not been called");
+    if (!out_rgb) return fail(ctx, RTW_E_INVALID_ARG, "out_rgb is NULL");
+    ctx->prog = ProgressiveState{};  // the accumulators are reused
+    const int H = rtw_image_height(W);
+    const int G = (int)ctx->dev.size();
+    const size_t img_vals = (size_t)W * (size_t)H * 3;
+    const int fx_bits = fx_bits_for(spp);
+    const bool timing = ctx->collect_timing != 0;
+    DeviceState& d0 = ctx->dev[0];
+    int rc;
+    RTW_CUDA(ctx, cudaSetDevice(d0.device));
+    rc = grow(ctx, &d0.d_image64, &d0.image64_cap, img_vals);
+    if (rc) return rc;
+    if (!scene_uploaded_in_call) RTW_CUDA(ctx, cudaEventRecord(d0.ev[3], d0.stream));
+    RTW_CUDA(ctx, cudaEventRecord(d0.ev[6], d0.stream));
+    const int rows_pad = (H + G - 1) / G;
+    const size_t tile_vals = (size_t)rows_pad * W * 3;
+    if (G > 1) {
+        rc = grow(ctx, &d0.d_gather64, &d0.gather64_cap, tile_vals * G);
+        if (rc) return rc;
+    }
+    for (int g = 0; g < G; ++g) {
+        DeviceState& ds = ctx->dev[g];
+        RTW_CUDA(ctx, cudaSetDevice(ds.device));
+        const int n_rows = rows_of(H, g, G);
+        ds.last = rtw_stats{};
+        ds.last.n_spheres = ctx->n_spheres64;
+        ds.last.image_width = W;
+        ds.last.image_height = H;
+        ds.last.rows_rendered = n_rows;
+        ds.last.paths = (uint64_t)n_rows * (uint64_t)W * (uint64_t)spp;
+        ds.last_stream = ds.stream;
+        ds.last_valid = true;
+        ds.last_resolved = false;
+        ds.h_counters[1] = 0;
+        if (n_rows == 0) continue;
+        const size_t npix = (size_t)n_rows * (size_t)W;
+        rc = grow(ctx, &ds.d_accum, &ds.accum_cap, npix * 4);
+        if (rc) return rc;
+        if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[0], ds.stream));
+        RTW_CUDA(ctx, cudaMemsetAsync(ds.d_accum, 0, npix * 4 * sizeof(unsigned long long), ds.stream));
+        RTW_CUDA(ctx, cudaMemsetAsync(ds.d_counters, 0, 2 * sizeof(unsigned long long), ds.stream));
+        int launches = 0;
+        if (max_depth > 0) {
+            rtw::TraceParams64 p;
+            for (int k = 0; k < 3; ++k) {
+                p.cam.origin[k] = cam->origin[k];
+                p.cam.llc[k] = cam->lower_left_corner[k];
+                p.cam.horizontal[k] = cam->horizontal[k];
+                p.cam.vertical[k] = cam->vertical[k];
+                p.cam.u[k] = cam->u[k];
+                p.cam.v[k] = cam->v[k];
+            }
+            p.cam.lens_radius = cam->lens_radius;
+            p.geom = ds.d_geom64;
+            p.mat = ds.d_mat64;
+            p.kind = ds.d_kind64;
+            p.n_spheres = ctx->n_spheres64;
+            p.W = W; p.H = H; p.spp = spp; p.max_depth = max_depth; p.sample_first = 0;
+            p.key0 = (uint32_t)seed; p.key1 = (uint32_t)(seed >> 32);
+            p.row_start = g; p.row_stride = G; p.n_rows = n_rows;
+            p.n_paths = (unsigned long long)npix * (unsigned long long)spp;
+            p.accum = ds.d_accum;
+            p.fx_scale = std::ldexp(1.0, fx_bits);
+            p.counters = ds.d_counters;
+            rtw::LaunchInfo li{};
+            RTW_CUDA(ctx, rtw::launch_trace_f64(p, ds.num_sms, ds.stream, &li));
+            launches += li.launches;
+        }
+        if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[1], ds.stream));
+        RTW_CUDA(ctx, cudaMemcpyAsync(ds.h_counters, ds.d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                      ds.stream));
+        double* dst = G == 1 ? d0.d_image64 : d0.d_gather64 + tile_vals * g;
+        double* tile = dst;
+        if (g != 0) {
+            rc = grow(ctx, &ds.d_tile64, &ds.tile64_cap, tile_vals);
+            if (rc) return rc;
+            tile = ds.d_tile64;
+        }
+        RTW_CUDA(ctx, rtw::launch_resolve_f64(ds.d_accum, W, H, n_rows, g, G, spp, std::ldexp(1.0, -fx_bits), G == 1 ? 1 : 0,
+                                              tile, ds.stream));
+        launches += 1;
+        if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[2], ds.stream));
+        ds.last_resolved = true;
+        ds.last.kernel_launches = launches;
+        if (g != 0) {
+            const size_t bytes = (size_t)n_rows * W * 3 * sizeof(double);
+            RTW_CUDA(ctx, cudaMemcpyPeerAsync(dst, d0.device, tile, ds.device, bytes, ds.stream));
+            RTW_CUDA(ctx, cudaEventRecord(ds.ev_tile, ds.stream));
+        }
+    }
+    RTW_CUDA(ctx, cudaSetDevice(d0.device));
+    if (G > 1) {
+        for (int g = 1; g < G; ++g) RTW_CUDA(ctx, cudaStreamWaitEvent(d0.stream, ctx->dev[g].ev_tile, 0));
+        RTW_CUDA(ctx, rtw::launch_assemble_f64(d0.d_gather64, G, W, H, d0.d_image64, d0.stream));
+    }
+    RTW_CUDA(ctx, cudaEventRecord(d0.ev[4], d0.stream));
+    if (img_vals)
+        RTW_CUDA(ctx, cudaMemcpyAsync(out_rgb, d0.d_image64, img_vals * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
+    RTW_CUDA(ctx, cudaEventRecord(d0.ev[5], d0.stream));
+    for (int g = G - 1; g >= 0; --g) {
+        RTW_CUDA(ctx, cudaSetDevice(ctx->dev[g].device));
+        RTW_CUDA(ctx, cudaStreamSynchronize(ctx->dev[g].stream));
+    }
+    rtw_stats total = {};
+    total.n_spheres = ctx->n_spheres64;
+    total.image_width = W;
+    total.image_height = H;
+    for (int g = 0; g < G; ++g) {
+        DeviceState& ds = ctx->dev[g];
+        RTW_CUDA(ctx, cudaSetDevice(ds.device));
+        ds.last.ray_segments = ds.h_counters[1];
+        ds.last.sphere_tests = ds.last.ray_segments * (uint64_t)ctx->n_spheres64;
+        if (timing && ds.last.rows_rendered > 0) {
+            float a = 0.f, b = 0.f;
+            RTW_CUDA(ctx, cudaEventElapsedTime(&a, ds.ev[0], ds.ev[1]));
+            RTW_CUDA(ctx, cudaEventElapsedTime(&b, ds.ev[1], ds.ev[2]));
+            ds.last.ms_trace = a;
+            ds.last.ms_resolve = b;
+        }
+        total.paths += ds.last.paths;
+        total.ray_segments += ds.last.ray_segments;
+        total.sphere_tests += ds.last.sphere_tests;
+        total.rows_rendered += ds.last.rows_rendered;
+        total.kernel_launches += ds.last.kernel_launches;
+        total.ms_trace = std::fmax(total.ms_trace, ds.last.ms_trace);
+        total.ms_resolve = std::fmax(total.ms_resolve, ds.last.ms_resolve);
+    }
+    if (G > 1) total.kernel_launches += 1;
+    RTW_CUDA(ctx, cudaSetDevice(d0.device));
+    float ms = 0.f;
+    RTW_CUDA(ctx, cudaEventElapsedTime(&ms, d0.ev[3], d0.ev[5]));
+    total.ms_total = ms;
+    RTW_CUDA(ctx, cudaEventElapsedTime(&ms, d0.ev[4], d0.ev[5]));
+    total.ms_d2h = ms;
+    RTW_CUDA(ctx, cudaEventElapsedTime(&ms, d0.ev[3], d0.ev[6]));
+    total.ms_h2d = ms;
+    if (stats) *stats = total;
+    return RTW_OK;
+}
+
 }  // namespace
 
 // ================================================================================================ C-ABI
@@ -609,6 +801,8 @@ int rtw_destroy(rtw_ctx* ctx) {
         if (ds.stream) cudaStreamSynchronize(ds.stream);
         cudaFree(ds.d_geom); cudaFree(ds.d_geom_pairs); cudaFree(ds.d_mat); cudaFree(ds.d_kind);
         cudaFree(ds.d_geom_perm[0]); cudaFree(ds.d_geom_perm[1]); cudaFree(ds.d_uv);
+        cudaFree(ds.d_geom64); cudaFree(ds.d_mat64); cudaFree(ds.d_kind64);
+        cudaFree(ds.d_tile64); cudaFree(ds.d_gather64); cudaFree(ds.d_image64);
         cudaFree(ds.d_accum); cudaFree(ds.d_counters); cudaFree(ds.d_tile);
         cudaFree(ds.d_gather); cudaFree(ds.d_image); cudaFree(ds.d_rgb8); cudaFree(ds.d_scratch); cudaFree(ds.d_wf);
         if (ds.h_counters) cudaFreeHost(ds.h_counters);
@@ -755,6 +949,44 @@ int rtw_assemble_tiles_device(rtw_ctx* ctx, int device_slot, const float* d_tile
     cudaStream_t s = stream ? (cudaStream_t)stream : ds.stream;
     RTW_CUDA(ctx, rtw::launch_assemble(d_tiles, n_tiles, image_width, rtw_image_height(image_width), d_out_rgb, s));
     return RTW_OK;
+}
+
+int rtw_set_scene_f64(rtw_ctx* ctx, const double* geom4, const double* mat4, const uint32_t* kind, uint32_t n_spheres) {
+    if (!ctx) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    try {
+        return set_scene_f64_locked(ctx, geom4, mat4, kind, n_spheres);
+    } catch (...) {
+        return fail(ctx, RTW_E_INTERNAL, "unexpected C++ exception in rtw_set_scene_f64");
+    }
+}
+
+int rtw_render_f64(rtw_ctx* ctx, const rtw_camera_f64* cam, int image_width, int n_samples, int max_depth, uint64_t seed,
+                   double* out_rgb, rtw_stats* stats) {
+    if (!ctx) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    try {
+        return render_f64_locked(ctx, cam, image_width, n_samples, max_depth, seed, out_rgb, stats, false);
+    } catch (...) {
+        return fail(ctx, RTW_E_INTERNAL, "unexpected C++ exception in rtw_render_f64");
+    }
+}
+
+int rtw_render_scene_f64(rtw_ctx* ctx, const double* geom4, const double* mat4, const uint32_t* kind, uint32_t n_spheres,
+                         const rtw_camera_f64* cam, int image_width, int n_samples, int max_depth, uint64_t seed,
+                         double* out_rgb, rtw_stats* stats) {
+    if (!ctx) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    try {
+        DeviceState& d0 = ctx->dev[0];
+        RTW_CUDA(ctx, cudaSetDevice(d0.device));
+        RTW_CUDA(ctx, cudaEventRecord(d0.ev[3], d0.stream));
+        int rc = set_scene_f64_locked(ctx, geom4, mat4, kind, n_spheres);
+        if (rc) return rc;
+        return render_f64_locked(ctx, cam, image_width, n_samples, max_depth, seed, out_rgb, stats, true);
+    } catch (...) {
+        return fail(ctx, RTW_E_INTERNAL, "unexpected C++ exception in rtw_render_scene_f64");
+    }
 }
 
 int rtw_accumulate(rtw_ctx* ctx, const rtw_camera* cam, int image_width, int sample_first, int sample_count,

@@ -1,0 +1,310 @@
+// rtw_f64.cu -- the Float64 instantiation of the hot path.
+//
+// The reference is generic over T (src/scenes.jl:2 `elem_type`, src/camera.jl:38) and its own test and every
+// timing it publishes use Float64 (test/runtests.jl:190-194, README.md:86-122).  This file is the same persistent
+// fused kernel -- regenerate -> closest-hit sweep -> shade/scatter -> accumulate -- written for T = Float64 on the
+// FP64 pipe (DADD/DMUL/DFMA; B200 issues them at half the FP32 rate), so that a Camera{Float64} / Float64 scene is
+// served by the GPU instead of being refused.  It follows the reference functions line for line like the Float32
+// path (rtw_device.cuh) and the same floating-point contract: dot = fma(z,z, fma(y,y, x*x)), a +- b*c is one fma,
+// sqrt and / are IEEE, normalize(v) = v * (1/sqrt(v.v)); -fmad=false, nothing else is contracted.
+//
+// Stream: the same addressed Philox4x32-10, a Float64 draw takes two words (u64 = hi:lo, f64 = (u64 >> 12) * 2^-52,
+// RandomNumbers-style 52 random mantissa bits):  draw n of an event = words (2(n&1), 2(n&1)+1) of block n >> 1.
+//   event 0: draws 0,1 = jitter; disk attempt k = draws 2+2k, 3+2k (block 1+k)
+//   event e: ball attempt a = draws 4a, 4a+1, 4a+2 (blocks 2a, 2a+1); draw 3 = dielectric coin (block 1, words 2,3)
+// The sweep is the straightforward one (test, then select the root under a branch, in list order): at half-rate
+// FP64 arithmetic the per-test overhead the Float32 kernel works to remove is proportionally small.
+#include "rtw_kernels.h"
+#include "rtw_sweep.cuh"
+
+namespace rtw {
+
+namespace {
+
+struct d3 {
+    double x, y, z;
+};
+__device__ __forceinline__ d3 mkd(double x, double y, double z) { return d3{x, y, z}; }
+__device__ __forceinline__ double dotd(d3 a, d3 b) { return fma(a.z, b.z, fma(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ d3 normalized(d3 a) {
+    const double inv = 1.0 / sqrt(dotd(a, a));  // StaticArrays 1.2.13: inv(norm(v)) * v
+    return mkd(a.x * inv, a.y * inv, a.z * inv);
+}
+// trand(Float64), src/rand.jl:10-13: 52 random mantissa bits
+__device__ __forceinline__ double u01d(uint32_t lo, uint32_t hi) {
+    return (double)((((unsigned long long)hi << 32) | lo) >> 12) * 2.220446049250313e-16;  // 2^-52
+}
+__device__ __forceinline__ double pm1d(uint32_t lo, uint32_t hi) { return fma(u01d(lo, hi), 2.0, -1.0); }  // rand.jl:24
+
+__device__ __forceinline__ d3 reflectd(d3 v, d3 n) {  // src/light.jl:6
+    const double k = 2.0 * dotd(v, n);
+    return mkd(fma(-k, n.x, v.x), fma(-k, n.y, v.y), fma(-k, n.z, v.z));
+}
+
+// normalize(random_vec3_in_sphere), src/rand.jl:15-22,29
+__device__ __forceinline__ d3 unit_vector_d(const PathRng& g, uint32_t event, uint32_t k0, uint32_t k1) {
+    for (uint32_t a = 0;; ++a) {
+        const u32x4 b0 = philox_block(g, event, 2u * a, k0, k1);
+        const u32x4 b1 = philox_block(g, event, 2u * a + 1u, k0, k1);
+        const d3 p = mkd(pm1d(b0.w0, b0.w1), pm1d(b0.w2, b0.w3), pm1d(b1.w0, b1.w1));
+        if (dotd(p, p) <= 1.0) return normalized(p);
+    }
+}
+
+template <bool kShared>
+__global__ void __launch_bounds__(kTraceBlock, 2) trace_f64_kernel(const __grid_constant__ TraceParams64 P) {
+    extern __shared__ __align__(16) unsigned char smem_raw64[];
+    double4* s_geom = reinterpret_cast<double4*>(smem_raw64);
+    const uint32_t n = P.n_spheres;
+    if (kShared) {
+        for (uint32_t i = threadIdx.x; i < n; i += kTraceBlock) s_geom[i] = P.geom[i];
+        __syncthreads();
+    }
+    const double4* __restrict__ list = kShared ? s_geom : P.geom;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t k0 = P.key0, k1 = P.key1;
+    const double tmin = 1e-4;  // T(1e-4), src/ray_color.jl:19
+
+    d3 o = mkd(0, 0, 0), d = mkd(0, 1, 0);
+    double thr_r = 1.0, thr_g = 1.0, thr_b = 1.0;
+    uint32_t pix_local = 0u, nhits = 0u;
+    PathRng rng{0u, 0u};
+    bool alive = false, done = false;
+    uint32_t seg_count = 0;
+    unsigned long long pool_next = 0, pool_end = 0;
+    bool exhausted = false;
+
+    for (;;) {
+        // ---- regenerate: idle lanes take the next path ticket (src/render.jl:24-37)
+        {
+            bool want = !alive && !done;
+            unsigned pending = __ballot_sync(kFullMask, want);
+            unsigned long long ticket = 0;
+            bool got = false;
+            while (pending) {
+                if (exhausted) {
+                    if (want) { done = true; want = false; }
+                    break;
+                }
+                if (pool_next >= pool_end) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(P.counters, (unsigned long long)kPoolChunk);
+                    base = __shfl_sync(kFullMask, base, 0);
+                    if (base >= P.n_paths) { exhausted = true; continue; }
+                    pool_next = base;
+                    pool_end = base + kPoolChunk < P.n_paths ? base + kPoolChunk : P.n_paths;
+                }
+                const unsigned avail = (unsigned)(pool_end - pool_next);
+                const unsigned rank = __popc(pending & lt_mask);
+                if (want && rank < avail) { ticket = pool_next + rank; want = false; got = true; }
+                const unsigned npend = __popc(pending);
+                pool_next += npend < avail ? npend : avail;
+                pending = __ballot_sync(kFullMask, want);
+            }
+            if (got) {
+                const unsigned long long q = ticket / (unsigned)P.spp;
+                const uint32_t pl = (uint32_t)q;
+                const uint32_t s0 = (uint32_t)(ticket - q * (unsigned)P.spp) + (uint32_t)P.sample_first;
+                const uint32_t row_local = pl / (uint32_t)P.W, col = pl - row_local * (uint32_t)P.W;
+                const uint32_t i0 = (uint32_t)P.row_start + row_local * (uint32_t)P.row_stride;
+                double s = (double)(col + 1u) / (double)P.W;                  // u = T(j/W), src/render.jl:26
+                double t = (double)((uint32_t)P.H - 1u - i0) / (double)P.H;   // v = T((H-i)/H), src/render.jl:27
+                rng.pixel = i0 * (uint32_t)P.W + col;
+                rng.sample = s0;
+                if (s0 != 0u) {  // src/render.jl:30-36: the first sample is centred; du = draw 0, dv = draw 1
+                    const u32x4 b = philox_block(rng, 0u, 0u, k0, k1);
+                    s += u01d(b.w0, b.w1) / (double)(float)P.W;
+                    t += u01d(b.w2, b.w3) / (double)(float)P.H;
+                }
+                // get_ray, src/camera.jl:43-48; random_vec2_in_disk (src/rand.jl:31-38) is always drawn
+                double px, py;
+                for (uint32_t k = 0;; ++k) {
+                    const u32x4 b = philox_block(rng, 0u, 1u + k, k0, k1);
+                    px = pm1d(b.w0, b.w1);
+                    py = pm1d(b.w2, b.w3);
+                    if (fma(py, py, px * px) <= 1.0) break;
+                }
+                const DevCamera64& c = P.cam;
+                const double rx = c.lens_radius * px, ry = c.lens_radius * py;
+                const d3 off = mkd(fma(c.v[0], ry, c.u[0] * rx), fma(c.v[1], ry, c.u[1] * rx), fma(c.v[2], ry, c.u[2] * rx));
+                o = mkd(c.origin[0] + off.x, c.origin[1] + off.y, c.origin[2] + off.z);
+                d3 q3;
+                q3.x = fma(t, c.vertical[0], fma(s, c.horizontal[0], c.llc[0])) - c.origin[0] - off.x;
+                q3.y = fma(t, c.vertical[1], fma(s, c.horizontal[1], c.llc[1])) - c.origin[1] - off.y;
+                q3.z = fma(t, c.vertical[2], fma(s, c.horizontal[2], c.llc[2])) - c.origin[2] - off.z;
+                d = normalized(q3);
+                thr_r = thr_g = thr_b = 1.0;
+                nhits = 0u;
+                pix_local = pl;
+                alive = true;
+            }
+        }
+        if (__ballot_sync(kFullMask, alive) == 0u) break;
+
+        // ---- intersect: hit(::HittableList), src/hit.jl:38-50, hit(::Sphere) src/hit.jl:12-35
+        double best_t = __longlong_as_double(0x7ff0000000000000ll);  // typemax(T)
+        int best_k = -1;
+#pragma unroll 2
+        for (uint32_t k = 0; k < n; ++k) {
+            const double4 s = list[k];
+            const d3 oc = mkd(o.x - s.x, o.y - s.y, o.z - s.z);
+            const double hb = dotd(oc, d);
+            const double cq = fma(-s.w, s.w, dotd(oc, oc));
+            const double disc = fma(hb, hb, -cq);
+            if (!(disc < 0.0) && alive) {  // src/hit.jl:19
+                const double sq = sqrt(disc);
+                double root = -hb - sq;
+                if (root < tmin || best_t < root) {
+                    root = -hb + sq;
+                    if (root < tmin || best_t < root) continue;
+                }
+                best_t = root;  // ties: the later sphere wins (inclusive range test)
+                best_k = (int)k;
+            }
+        }
+
+        // ---- shade / scatter / accumulate
+        if (alive) {
+            seg_count += 1;
+            if (best_k < 0) {  // miss: skycolor, src/ray_color.jl:1-6 (no contraction)
+                const double t = 0.5 * (d.y + 1.0);
+                const double a = 1.0 - t;
+                const double sr = a + t * 0.5, sg = a + t * 0.7, sb = a + t;
+                unsigned long long* acc = P.accum + (unsigned long long)pix_local * 4ull;
+                atomicAdd(acc + 0, (unsigned long long)__double2ll_rn(thr_r * sr * P.fx_scale));
+                atomicAdd(acc + 1, (unsigned long long)__double2ll_rn(thr_g * sg * P.fx_scale));
+                atomicAdd(acc + 2, (unsigned long long)__double2ll_rn(thr_b * sb * P.fx_scale));
+                alive = false;
+            } else if (++nhits == (uint32_t)P.max_depth) {
+                alive = false;  // the next ray_color call returns black, src/ray_color.jl:15-17
+            } else {
+                const double4 g = P.geom[best_k];
+                const double4 m = P.mat[best_k];
+                const uint32_t kind = __ldg(P.kind + best_k);
+                const d3 p = mkd(fma(best_t, d.x, o.x), fma(best_t, d.y, o.y), fma(best_t, d.z, o.z));  // hit.jl:3
+                const d3 on = mkd((p.x - g.x) / g.w, (p.y - g.y) / g.w, (p.z - g.z) / g.w);             // hit.jl:33
+                const bool front = dotd(d, on) < 0.0;                                                  // hit.jl:7
+                const d3 nn = front ? on : mkd(-on.x, -on.y, -on.z);
+                d3 nd;
+                if (kind == 0u) {  // Lambertian, src/material.jl:13-23
+                    const d3 rv = unit_vector_d(rng, nhits, k0, k1);
+                    const d3 sd = mkd(nn.x + rv.x, nn.y + rv.y, nn.z + rv.z);
+                    nd = dotd(sd, sd) < 1e-5 ? nn : normalized(sd);  // near_zero, src/vec.jl:20
+                } else if (kind == 1u) {  // Metal, src/material.jl:31-34
+                    const d3 refl = reflectd(d, nn);
+                    const d3 rv = unit_vector_d(rng, nhits, k0, k1);
+                    nd = normalized(mkd(fma(m.w, rv.x, refl.x), fma(m.w, rv.y, refl.y), fma(m.w, rv.z, refl.z)));
+                } else {  // Dielectric, src/material.jl:41-53
+                    const double ratio = front ? 1.0 / m.w : m.w;
+                    const double cos_t = fmin(-dotd(d, nn), 1.0);
+                    const double sin_t = sqrt(fma(-cos_t, cos_t, 1.0));
+                    bool reflects = ratio * sin_t > 1.0;
+                    if (!reflects) {  // `||` short-circuits: the coin is drawn only when refraction is possible
+                        const u32x4 b = philox_block(rng, nhits, 1u, k0, k1);
+                        double r0 = (1.0 - ratio) / (1.0 + ratio);  // Schlick, src/light.jl:19-25
+                        r0 = r0 * r0;
+                        const double x = 1.0 - cos_t, x2 = x * x, x4 = x2 * x2;
+                        reflects = fma(1.0 - r0, x4 * x, r0) > u01d(b.w2, b.w3);
+                    }
+                    if (reflects) {
+                        nd = reflectd(d, nn);  // not re-normalised, src/material.jl:48
+                    } else {  // refract, src/light.jl:12-17
+                        const d3 perp = mkd(ratio * fma(cos_t, nn.x, d.x), ratio * fma(cos_t, nn.y, d.y),
+                                            ratio * fma(cos_t, nn.z, d.z));
+                        const double sp = sqrt(fabs(1.0 - dotd(perp, perp)));
+                        nd = normalized(mkd(fma(-sp, nn.x, perp.x), fma(-sp, nn.y, perp.y), fma(-sp, nn.z, perp.z)));
+                    }
+                }
+                if (kind != 2u) {  // attenuation = albedo (Dielectric: ones)
+                    thr_r *= m.x;
+                    thr_g *= m.y;
+                    thr_b *= m.z;
+                }
+                o = p;
+                d = nd;
+            }
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) seg_count += __shfl_xor_sync(kFullMask, seg_count, off);
+    if (lane == 0 && seg_count) atomicAdd(P.counters + 1, (unsigned long long)seg_count);
+}
+
+// accum / n_samples -> sqrt (src/render.jl:40, src/vec.jl:22), Float64 out: tile row-major or Julia column-major
+__global__ void __launch_bounds__(256) resolve_f64_kernel(const unsigned long long* __restrict__ accum, int W, int H,
+                                                          int n_rows, int row_start, int row_stride, int spp,
+                                                          double inv_scale, int column_major, double* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n_rows * W) return;
+    int k, col;
+    if (column_major) { col = (int)(t / n_rows); k = (int)(t - (long long)col * n_rows); }
+    else { k = (int)(t / W); col = (int)(t - (long long)k * W); }
+    const unsigned long long* a = accum + ((long long)k * W + col) * 4;
+    const long long at = column_major ? ((long long)col * H + (row_start + (long long)k * row_stride)) * 3
+                                      : ((long long)k * W + col) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[at + c] = sqrt((double)(long long)a[c] * inv_scale / (double)spp);
+}
+
+__global__ void __launch_bounds__(256) assemble_f64_kernel(const double* __restrict__ tiles, int G, int W, int H,
+                                                           int rows_pad, double* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)W * H) return;
+    const int col = (int)(t / H), i0 = (int)(t - (long long)col * H);
+    const int g = i0 % G, k = i0 / G;
+    const double* src = tiles + (((long long)g * rows_pad + k) * W + col) * 3;
+    out[t * 3 + 0] = src[0];
+    out[t * 3 + 1] = src[1];
+    out[t * 3 + 2] = src[2];
+}
+
+}  // namespace
+
+cudaError_t launch_trace_f64(const TraceParams64& p, int num_sms, cudaStream_t stream, LaunchInfo* info) {
+    const bool shared = p.n_spheres <= kTileSpheres;
+    const int smem = shared ? (int)(p.n_spheres * sizeof(double4)) : 0;
+    cudaError_t e = cudaSuccess;
+    int per_sm = 0;
+    if (shared) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_f64_kernel<true>, kTraceBlock, smem);
+    } else {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_f64_kernel<false>, kTraceBlock, 0);
+    }
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)num_sms * per_sm;
+    const long long max_useful = (long long)((p.n_paths + (unsigned long long)kTraceBlock - 1ull) / (unsigned long long)kTraceBlock);
+    if (grid > max_useful) grid = max_useful;
+    if (grid < 1) grid = 1;
+    if (shared) trace_f64_kernel<true><<<(unsigned)grid, kTraceBlock, smem, stream>>>(p);
+    else trace_f64_kernel<false><<<(unsigned)grid, kTraceBlock, 0, stream>>>(p);
+    if (info) {
+        info->grid = (int)grid;
+        info->block = kTraceBlock;
+        info->smem_bytes = smem;
+        info->blocks_per_sm = per_sm;
+        info->launches = 1;
+        info->rays_per_lane = 1;
+        info->sweep = kSweepBranch;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resolve_f64(const unsigned long long* accum, int W, int H, int n_rows, int row_start, int row_stride,
+                               int spp, double inv_scale, int column_major, double* out, cudaStream_t stream) {
+    const long long total = (long long)n_rows * W;
+    if (total <= 0) return cudaSuccess;
+    resolve_f64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(accum, W, H, n_rows, row_start, row_stride, spp,
+                                                                             inv_scale, column_major, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assemble_f64(const double* tiles, int n_tiles, int W, int H, double* out, cudaStream_t stream) {
+    const long long total = (long long)W * H;
+    if (total <= 0) return cudaSuccess;
+    const int rows_pad = (H + n_tiles - 1) / n_tiles;
+    assemble_f64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(tiles, n_tiles, W, H, rows_pad, out);
+    return cudaGetLastError();
+}
+
+}  // namespace rtw

@@ -43,6 +43,27 @@ struct TraceParams {
     unsigned long long* counters;
 };
 
+// Float64 instantiation (rtw_f64.cu): Camera{Float64} fields get_ray reads, scene as double4 arrays
+struct DevCamera64 {
+    double origin[3], llc[3], horizontal[3], vertical[3], u[3], v[3];
+    double lens_radius;
+};
+
+struct TraceParams64 {
+    DevCamera64 cam;
+    const double4* geom;  // n x {cx,cy,cz,r}
+    const double4* mat;   // n x {albedo rgb, fuzz|ir}
+    const uint32_t* kind;
+    uint32_t n_spheres;
+    int W, H, spp, max_depth, sample_first;
+    uint32_t key0, key1;
+    int row_start, row_stride, n_rows;
+    unsigned long long n_paths;
+    unsigned long long* accum;
+    double fx_scale;
+    unsigned long long* counters;
+};
+
 // RTW_MODE_WAVEFRONT: the path pool in HBM (structure of arrays over `capacity` slots) and its work lists
 struct WavefrontBuffers {
     uint32_t capacity;
@@ -92,6 +113,11 @@ cudaError_t launch_resolve(const unsigned long long* accum, int W, int H, int n_
 cudaError_t launch_assemble(const float* tiles, int n_tiles, int W, int H, float* out, cudaStream_t stream);
 // Julia column-major Float32 image -> row-major 8-bit RGB, clamp01nan + N0f8 rounding (rtw_image.cu)
 cudaError_t launch_quantize_rgb8(const float* img, int W, int H, unsigned char* out, cudaStream_t stream);
+// Float64 path (rtw_f64.cu)
+cudaError_t launch_trace_f64(const TraceParams64& p, int num_sms, cudaStream_t stream, LaunchInfo* info);
+cudaError_t launch_resolve_f64(const unsigned long long* accum, int W, int H, int n_rows, int row_start, int row_stride,
+                               int spp, double inv_scale, int column_major, double* out, cudaStream_t stream);
+cudaError_t launch_assemble_f64(const double* tiles, int n_tiles, int W, int H, double* out, cudaStream_t stream);
 // FP32 issue microbenchmarks; returns lane-instructions executed through *fp32_instr
 cudaError_t launch_fp32_peak(int variant, int num_sms, float* scratch, cudaStream_t stream, double* fp32_instr);
 

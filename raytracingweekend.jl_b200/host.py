@@ -148,11 +148,12 @@ class HittableList(list):
 KIND_LAMBERTIAN, KIND_METAL, KIND_DIELECTRIC = 0, 1, 2
 
 
-def flatten_scene(scene: Sequence[Sphere]) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+def flatten_scene(scene: Sequence[Sphere], elem_type=F32) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Flatten a HittableList into the SoA arrays of the C-ABI (include/rtw_b200.h, rtw_set_scene):
     geom4 = n x {cx,cy,cz,r}, mat4 = n x {albedo rgb, fuzz|ir|0}, kind = n x u32.  List order is kept.
     This is the one piece of glue the Julia shim also needs (Sphere.mat is abstract => not isbits)."""
     n = len(scene)
+    F32 = elem_type  # noqa: N806 -- element type of the flattened arrays (Float32 by default, Float64 for the f64 path)
     geom = np.zeros((n, 4), dtype=F32)
     mat = np.zeros((n, 4), dtype=F32)
     kind = np.zeros((n,), dtype=np.uint32)

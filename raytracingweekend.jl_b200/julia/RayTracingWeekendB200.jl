@@ -116,8 +116,41 @@ function render_b200(scene::HittableList, cam::Camera{Float32}, image_width::Int
     img
 end
 
-render_b200(scene::HittableList, cam::Camera, args...; kw...) =
-    error("rtw_b200: only Camera{Float32} is supported on the CUDA path (there is no CPU fallback)")
+# ---- Camera{Float64}: the Float64 instantiation of the kernels (rtw_render_scene_f64) ---------------------------
+matrow64(m::Lambertian{Float64}) = (RTW_LAMBERTIAN, (m.albedo[1], m.albedo[2], m.albedo[3], 0.0))
+matrow64(m::Metal{Float64})      = (RTW_METAL,      (m.albedo[1], m.albedo[2], m.albedo[3], m.fuzz))
+matrow64(m::Dielectric{Float64}) = (RTW_DIELECTRIC, (1.0, 1.0, 1.0, m.ir))
+matrow64(m) = error("rtw_b200: unsupported material $(typeof(m)) in a Float64 scene")
+
+function flatten64(scene::HittableList)
+    n = length(scene)
+    geom, mat, kind = Matrix{Float64}(undef, 4, n), Matrix{Float64}(undef, 4, n), Vector{UInt32}(undef, n)
+    for (k, s) in enumerate(scene)
+        s isa Sphere{Float64} || error("rtw_b200: a Float64 camera needs Sphere{Float64} hittables, got $(typeof(s))")
+        geom[1, k], geom[2, k], geom[3, k] = s.center
+        geom[4, k] = s.radius
+        kind[k], row = matrow64(s.mat)
+        mat[:, k] .= row
+    end
+    geom, mat, kind
+end
+
+function render_b200(scene::HittableList, cam::Camera{Float64}, image_width::Integer = 400, n_samples::Integer = 1;
+                     max_depth::Integer = 16, seed::Integer = 1, ctx::Context = default_context(),
+                     stats::Union{Nothing,Ref{RtwStats}} = nothing)
+    geom, mat, kind = flatten64(scene)
+    H = Int(ccall((:rtw_image_height, librtw), Cint, (Cint,), image_width))
+    img = Matrix{RGB{Float64}}(undef, H, image_width)
+    st = stats === nothing ? Ref{RtwStats}() : stats
+    camref = Ref(cam)                                      # Camera{Float64} is isbits: 22 x Float64 = rtw_camera_f64
+    GC.@preserve geom mat kind img camref begin
+        check(ctx.ptr, ccall((:rtw_render_scene_f64, librtw), Cint,
+                             (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt32}, UInt32, Ptr{Cvoid}, Cint, Cint, Cint, UInt64,
+                              Ptr{Cvoid}, Ptr{RtwStats}),
+                             ctx.ptr, geom, mat, kind, length(kind), camref, image_width, n_samples, max_depth, seed, img, st))
+    end
+    img
+end
 
 # ---- progressive rendering, image and scene files (C-ABI v2) ----------------------------------------------------
 # render() split into passes over the samples: every draw is addressed by (pixel, sample, event) and the accumulator
@@ -191,7 +224,7 @@ end
 
 # To make it a true drop-in, overload the reference's method for Float32 cameras:
 #     import RayTracingWeekend: render
-#     render(scene::HittableList, cam::Camera{Float32}, image_width=400, n_samples=1) =
+#     render(scene::HittableList, cam::Union{Camera{Float32},Camera{Float64}}, image_width=400, n_samples=1) =
 #         RayTracingWeekendB200.render_b200(scene, cam, image_width, n_samples)
 
 export render_b200, Context, RtwStats, set_scene!, accumulate!, resolve, save_png, save_scene, load_scene

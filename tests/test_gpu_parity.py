@@ -446,3 +446,60 @@ def test_progressive_passes_in_every_mode(rtw, renderer, scenes, mode, tail):
     finally:
         renderer.set_option(rtw.RTW_OPT_MODE, 0)
         renderer.set_option(rtw.RTW_OPT_TAIL, 0)
+
+
+F64_TOL = 1e-9  # Float64 image vs the oracle's Float64 instantiation (fixed-point accumulation quantum ~2^-46)
+
+
+def _f64_scene(rtw, name):
+    if name == "two":
+        return rtw.scene_2_spheres(elem_type=np.float64)
+    if name == "four":
+        return rtw.scene_4_spheres(elem_type=np.float64)
+    if name == "diel":
+        return rtw.scene_diel_spheres(elem_type=np.float64)
+    if name == "bubble":
+        return rtw.scene_diel_spheres(elem_type=np.float64) + [
+            rtw.Sphere(rtw.Vec3(-1, 0, -1, np.float64), -0.4, rtw.Dielectric(1.5))]
+    rtw.reseed()
+    return rtw.scene_random_spheres(elem_type=np.float64)
+
+
+@pytest.mark.parametrize("name,cam_name,W,spp,depth", [("two", "default", 96, 16, 16), ("four", "default", 96, 8, 16),
+                                                       ("diel", "cam2", 128, 16, 16), ("bubble", "default", 96, 8, 50),
+                                                       ("random", "cam1", 120, 8, 16)])
+def test_float64_path_matches_float64_oracle(rtw, oracle, renderer, name, cam_name, W, spp, depth):
+    # the reference's own test renders scene_2_spheres(Float64) with a Float64 camera at 96 x 16 spp
+    # (test/runtests.jl:190-194); the Float64 kernel follows the Float64 oracle path for path
+    cam = {"default": rtw.t_default_cam, "cam1": rtw.t_cam1, "cam2": rtw.t_cam2}[cam_name](np.float64)
+    scene = rtw.flatten_scene(_f64_scene(rtw, name), np.float64)
+    assert scene[0].dtype == np.float64
+    img = renderer.render(cam, W, spp, max_depth=depth, seed=3, scene=scene)
+    st = dict(renderer.last_stats)
+    ref, _, ost = oracle.render(*scene, cam.as_array(), W, spp, max_depth=depth, seed=3, f64=True)
+    assert img.dtype == np.float64 and img.shape == ref.shape
+    assert st["ray_segments"] == ost["ray_segments"]  # identical paths
+    assert float(np.abs(img - ref).max()) <= F64_TOL
+
+
+def test_float64_path_large_list_and_edges(rtw, oracle, renderer):
+    cam = rtw.t_cam1(np.float64)
+    rtw.reseed()
+    scene = rtw.flatten_scene(rtw.scene_random_spheres(elem_type=np.float64, half_extent=17), np.float64)  # > 1024: list read from HBM/L2
+    assert len(scene[2]) > 1024
+    img = renderer.render(cam, 64, 2, max_depth=8, scene=scene)
+    ref, _, ost = oracle.render(*scene, cam.as_array(), 64, 2, max_depth=8, f64=True)
+    assert renderer.last_stats["ray_segments"] == ost["ray_segments"] and float(np.abs(img - ref).max()) <= F64_TOL
+    empty = (np.zeros((0, 4)), np.zeros((0, 4)), np.zeros(0, np.uint32))
+    img = renderer.render(cam, 32, 2, scene=empty)
+    ref, _, _ = oracle.render(*empty, cam.as_array(), 32, 2, f64=True)
+    assert float(np.abs(img - ref).max()) <= F64_TOL
+    img = renderer.render(cam, 32, 2, max_depth=0, scene=scene)
+    assert not img.any()
+    # Float32 and Float64 scenes are held side by side
+    f32 = rtw.flatten_scene(rtw.scene_2_spheres())
+    a = np.array(renderer.render(rtw.t_default_cam(), 64, 2, scene=f32))
+    renderer.set_scene_f64(rtw.flatten_scene(rtw.scene_2_spheres(elem_type=np.float64), np.float64))
+    b = np.array(renderer.render(rtw.t_default_cam(np.float64), 64, 2))
+    assert np.array_equal(a, np.array(renderer.render(rtw.t_default_cam(), 64, 2)))
+    assert b.dtype == np.float64 and float(np.abs(a - b).mean()) < 0.05  # same scene; other stream words => other noise

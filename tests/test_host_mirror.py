@@ -60,7 +60,7 @@ def test_flatten_rejects_unknown(rtw):
     with pytest.raises(TypeError):
         rtw.flatten_scene([rtw.Sphere(rtw.Vec3(0, 0, 0), 1.0, "wood")])
     with pytest.raises(rtw.RtwError):
-        rtw.api._camera_struct(rtw.t_cam1(np.float64))  # Float64 cameras: unsupported, no CPU fallback
+        rtw.api._camera_struct(rtw.t_cam1(np.float64))  # the Float32 entry points refuse a Float64 camera (render() dispatches)
 
 
 def test_trand_range_and_reseed(rtw):

@@ -269,6 +269,7 @@ __device__ __forceinline__ void walk_own_ray_perm(const float4* __restrict__ aos
             bcode = code;
         }
     }
+    __syncwarp();  // all reads of the partners' mask words are done before the next sweep overwrites them
     best_t = bt;
     best_k = bcode != 0xffffffffu ? (int)perm_code_to_index(bcode, kCoop) : -1;
 }
@@ -556,6 +557,7 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
                 if (mine) { px = gx; py = gy; pz = gz; need = false; }
                 blk += per;
                 needm = __ballot_sync(kFullMask, need);
+                __syncwarp();  // every lane has read its request before the next pass overwrites the slots
             }
         }
 

@@ -503,3 +503,20 @@ def test_float64_path_large_list_and_edges(rtw, oracle, renderer):
     b = np.array(renderer.render(rtw.t_default_cam(np.float64), 64, 2))
     assert np.array_equal(a, np.array(renderer.render(rtw.t_default_cam(), 64, 2)))
     assert b.dtype == np.float64 and float(np.abs(a - b).mean()) < 0.05  # same scene; other stream words => other noise
+
+
+def test_more_than_2_32_paths_in_one_launch(rtw, renderer, scenes):
+    # full-size property (1920x1080, > 2^32 paths): one launch with 64-bit path tickets accumulates exactly the same
+    # integers as two launches that stay below 2^32 -- the ticket -> (pixel, sample) mapping, the addressed stream
+    # and the integer accumulator are the same on both sides of the 32-bit boundary
+    cam, W, total = rtw.t_cam1(), 1920, 2080
+    assert W * 1080 * total > 2 ** 32 > W * 1080 * (total // 2)
+    renderer.set_scene(scenes["two"])  # 2 spheres: the sweep is short, the ticket machinery is what is exercised
+    st = renderer.accumulate(cam, W, 0, total, total, max_depth=4, seed=2)
+    one = renderer.accumulator_read()
+    assert st["paths"] == W * 1080 * total
+    s1 = renderer.accumulate(cam, W, 0, total // 2, total, max_depth=4, seed=2)
+    s2 = renderer.accumulate(cam, W, total // 2, total - total // 2, total, max_depth=4, seed=2)
+    two = renderer.accumulator_read()
+    assert np.array_equal(one, two)
+    assert st["ray_segments"] == s1["ray_segments"] + s2["ray_segments"]

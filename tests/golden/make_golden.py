@@ -42,6 +42,13 @@ def main():
     # RNG stream vectors: first 8 uniforms of three paths
     streams = np.stack([O.path_stream(1, p, s, e, 8) for p, s, e in [(0, 0, 0), (12345, 7, 1), (2073599, 999, 50)]])
     np.save(HERE / "philox_path_streams_seed1.npy", streams)
+    # the reference's own smoke render, in its own element type: render(scene_2_spheres(Float64), default_cam, 96, 16)
+    # (test/runtests.jl:190-194), depth 16 -- pins the Float64 instantiation of the oracle and of the CUDA path
+    g, m, k = R.flatten_scene(R.scene_2_spheres(elem_type=np.float64), np.float64)
+    cam = R.t_default_cam(np.float64)
+    img, _, st = O.render(g, m, k, cam.as_array(), 96, 16, max_depth=16, seed=1, n_threads=1, f64=True)
+    np.savez_compressed(HERE / "runtests194_scene_2_spheres_f64_96x54_16spp_d16_seed1.npz", image=img, geom=g, mat=m, kind=k,
+                        camera=cam.as_array(), ray_segments=np.uint64(st["ray_segments"]))
     print("golden fixtures written to", HERE)
 
 

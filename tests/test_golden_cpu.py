@@ -33,3 +33,12 @@ def test_stream_fixture(oracle):
     gold = np.load(GOLD / "philox_path_streams_seed1.npy")
     for row, (p, s, e) in zip(gold, [(0, 0, 0), (12345, 7, 1), (2073599, 999, 50)]):
         assert np.array_equal(oracle.path_stream(1, p, s, e, 8), row)
+
+
+def test_float64_fixture_of_the_reference_smoke_render(oracle, rtw):
+    # test/runtests.jl:190-194: render(scene_2_spheres(Float64), default_camera, 96, 16)
+    gold = np.load(GOLD / "runtests194_scene_2_spheres_f64_96x54_16spp_d16_seed1.npz")
+    g, m, k = rtw.flatten_scene(rtw.scene_2_spheres(elem_type=np.float64), np.float64)
+    assert g.dtype == np.float64 and np.array_equal(g, gold["geom"]) and np.array_equal(m, gold["mat"])
+    img, _, st = oracle.render(g, m, k, gold["camera"], 96, 16, max_depth=16, seed=1, n_threads=2, f64=True)
+    assert img.dtype == np.float64 and np.array_equal(img, gold["image"]) and st["ray_segments"] == int(gold["ray_segments"])

@@ -520,3 +520,13 @@ def test_more_than_2_32_paths_in_one_launch(rtw, renderer, scenes):
     two = renderer.accumulator_read()
     assert np.array_equal(one, two)
     assert st["ray_segments"] == s1["ray_segments"] + s2["ray_segments"]
+
+
+def test_float64_golden_fixture(rtw, renderer):
+    # the reference's own smoke render (test/runtests.jl:190-194) in Float64, against the committed fixture
+    from pathlib import Path
+    gold = np.load(Path(__file__).parent / "golden" / "runtests194_scene_2_spheres_f64_96x54_16spp_d16_seed1.npz")
+    scene = (gold["geom"], gold["mat"], gold["kind"])
+    img = renderer.render(rtw.t_default_cam(np.float64), 96, 16, max_depth=16, seed=1, scene=scene)
+    assert float(np.abs(img - gold["image"]).max()) <= F64_TOL
+    assert renderer.last_stats["ray_segments"] == int(gold["ray_segments"])

@@ -114,6 +114,11 @@ typedef struct rtw_ctx rtw_ctx;
 
 #define RTW_MODE_FUSED 0          /* one persistent kernel: raygen -> {intersect, shade} loop -> accumulate */
 #define RTW_MODE_WAVEFRONT 1      /* separate raygen / intersect / shade / accumulate kernels + compaction  */
+#define RTW_MODE_GRID 3           /* the fused kernel with a uniform-grid traversal in place of the linear sweep: the same
+                                     closest hit and image bits from far fewer sphere tests (the reference is brute
+                                     force by design, README.md:30; acceleration structures are its long-term goal,
+                                     README.md:175).  Not the benchmarked path; rtw_stats.sphere_tests still reports
+                                     ray_segments * n_spheres, the tests the linear sweep would have made */
 #define RTW_MODE_CTA_WAVEFRONT 2  /* the same stages inside persistent CTAs: path pool + work lists in shared memory
                                      (lists <= 1024 spheres; larger lists fall back to RTW_MODE_FUSED)        */
 

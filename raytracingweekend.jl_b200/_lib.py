@@ -79,6 +79,7 @@ RTW_SWEEP_PACKED = 3
 RTW_MODE_FUSED = 0
 RTW_MODE_WAVEFRONT = 1
 RTW_MODE_CTA_WAVEFRONT = 2
+RTW_MODE_GRID = 3
 
 
 class RtwError(RuntimeError):

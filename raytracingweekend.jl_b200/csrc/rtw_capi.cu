@@ -2,6 +2,7 @@
 // No C++ exception leaves this file; every entry point returns a status code.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -30,6 +31,11 @@ struct DeviceState {
     float4* d_mat = nullptr;
     uint32_t* d_kind = nullptr;
     size_t scene_cap = 0;
+    // RTW_MODE_GRID: uniform grid over the scene (same content on every device)
+    uint32_t* d_grid_start = nullptr;
+    uint32_t* d_grid_items = nullptr;
+    uint32_t* d_grid_big = nullptr;
+    size_t grid_start_cap = 0, grid_items_cap = 0, grid_big_cap = 0;
     // Float64 scene and image buffers (rtw_*_f64)
     double4* d_geom64 = nullptr;
     double4* d_mat64 = nullptr;
@@ -81,6 +87,7 @@ struct rtw_ctx {
     bool have_scene = false;
     uint32_t n_spheres64 = 0;
     bool have_scene64 = false;
+    rtw::GridParams grid = {};  // host copy of the grid header (device pointers are per device)
     int mode = RTW_MODE_FUSED;
     int rays_per_lane = 0;  // 0 = default
     int sweep = 0;          // 0 = default
@@ -255,7 +262,25 @@ int enqueue_trace(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, i
         p.fx_scale = std::ldexp(1.0, fx_bits);
         p.counters = ds.d_counters;
         rtw::LaunchInfo li{};
-        if (ctx->mode == RTW_MODE_CTA_WAVEFRONT && ctx->n_spheres <= rtw::kTileSpheres) {
+        p.grid = ctx->grid;
+        p.grid.cell_start = ds.d_grid_start;
+        p.grid.items = ds.d_grid_items;
+        p.grid.big = ds.d_grid_big;
+        if (ctx->mode == RTW_MODE_GRID) {
+            rc = grow(ctx, &ds.d_uv, &ds.uv_cap, (size_t)W + (size_t)H);
+            if (rc) return rc;
+            RTW_CUDA(ctx, rtw::launch_uv_tables(W, H, ds.d_uv, ds.d_uv + W, stream));
+            launches += 1;
+            p.u_tab = ds.d_uv;
+            p.v_tab = ds.d_uv + W;
+            p.div_spp = rtw::make_magic_div((uint32_t)spp);
+            p.div_w = rtw::make_magic_div((uint32_t)W);
+            for (uint32_t r = 0; r < 10u; ++r) {
+                p.rk[2 * r] = p.key0 + r * rtw::kPhiloxW0;
+                p.rk[2 * r + 1] = p.key1 + r * rtw::kPhiloxW1;
+            }
+            RTW_CUDA(ctx, rtw::launch_fused_trace2_grid(p, ds.num_sms, ctx->blocks_per_sm, stream, &li));
+        } else if (ctx->mode == RTW_MODE_CTA_WAVEFRONT && ctx->n_spheres <= rtw::kTileSpheres) {
             RTW_CUDA(ctx, rtw::launch_cta_wavefront_trace(p, ds.num_sms, ctx->blocks_per_sm, stream, &li));
         } else if (ctx->mode == RTW_MODE_WAVEFRONT) {
             if (ctx->n_spheres > rtw::kTileSpheres)
@@ -339,6 +364,93 @@ int finish_stats(rtw_ctx* ctx, DeviceState& ds, bool timing) {
     return RTW_OK;
 }
 
+// RTW_MODE_GRID: bin the spheres (rtw_grid.cuh describes the structure and why the result is unchanged)
+struct HostGrid {
+    rtw::GridParams hdr = {};
+    std::vector<uint32_t> cell_start, items, big;
+};
+
+void build_grid(const float* geom4, uint32_t n, HostGrid* out) {
+    HostGrid& g = *out;
+    g = HostGrid{};
+    std::vector<float> radii(n);
+    for (uint32_t i = 0; i < n; ++i) radii[i] = std::fabs(geom4[4 * (size_t)i + 3]);
+    float r_med = 0.f;
+    if (n > 0) {
+        std::vector<float> tmp(radii);
+        std::nth_element(tmp.begin(), tmp.begin() + n / 2, tmp.end());
+        r_med = tmp[n / 2];
+    }
+    std::vector<uint32_t> small;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* s = geom4 + 4 * (size_t)i;
+        const bool finite = std::isfinite(s[0]) && std::isfinite(s[1]) && std::isfinite(s[2]) && std::isfinite(s[3]);
+        if (n <= 8 || !finite || !(r_med > 0.f) || radii[i] > 4.0f * r_med) g.big.push_back(i);  // every ray tests these
+        else small.push_back(i);
+    }
+    if (small.empty()) return;  // no grid: hdr.nx == 0
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (uint32_t i : small) {
+        const float* s = geom4 + 4 * (size_t)i;
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::min(lo[a], (double)s[a] - radii[i]);
+            hi[a] = std::max(hi[a], (double)s[a] + radii[i]);
+        }
+    }
+    double h = 2.5 * r_med;  // a small sphere (|r| <= 4 r_med) spans at most 5 cells per axis, typically 2
+    auto dims = [&](double hh, int* nd) {
+        double cells = 1.0;
+        for (int a = 0; a < 3; ++a) {
+            nd[a] = (int)std::floor((hi[a] - lo[a]) / hh) + 2;  // one cell of slack around the inflated boxes
+            cells *= nd[a];
+        }
+        return cells;
+    };
+    int nd[3];
+    while (dims(h, nd) > 2.0 * (double)small.size() + 64.0 || nd[0] > 1024 || nd[1] > 1024 || nd[2] > 1024) h *= 1.25;
+    const double inflate = 1e-3 * h;
+    g.hdr.h = (float)h;
+    g.hdr.inv_h = 1.0f / g.hdr.h;
+    g.hdr.ox = (float)(lo[0] - 0.5 * h);
+    g.hdr.oy = (float)(lo[1] - 0.5 * h);
+    g.hdr.oz = (float)(lo[2] - 0.5 * h);
+    g.hdr.nx = nd[0]; g.hdr.ny = nd[1]; g.hdr.nz = nd[2];
+    const double org[3] = {(double)g.hdr.ox, (double)g.hdr.oy, (double)g.hdr.oz};
+    const double hf = (double)g.hdr.h;  // the cell edge as the device sees it
+    auto range = [&](uint32_t i, int a, int* c0, int* c1) {
+        const float* s = geom4 + 4 * (size_t)i;
+        *c0 = std::min(std::max((int)std::floor(((double)s[a] - radii[i] - inflate - org[a]) / hf), 0), nd[a] - 1);
+        *c1 = std::min(std::max((int)std::floor(((double)s[a] + radii[i] + inflate - org[a]) / hf), 0), nd[a] - 1);
+    };
+    const size_t ncell = (size_t)nd[0] * nd[1] * nd[2];
+    g.cell_start.assign(ncell + 1, 0u);
+    for (int pass = 0; pass < 2; ++pass) {
+        std::vector<uint32_t> fill;
+        if (pass == 1) {
+            for (size_t c = 0, acc = 0; c <= ncell; ++c) {  // counts -> offsets
+                const uint32_t cnt = c < ncell ? g.cell_start[c] : 0u;
+                g.cell_start[c] = (uint32_t)acc;
+                acc += cnt;
+            }
+            g.items.assign(g.cell_start[ncell], 0u);
+            fill.assign(g.cell_start.begin(), g.cell_start.end() - 1);
+        }
+        for (uint32_t i : small) {  // ascending sphere index, so the items of a cell are ascending too
+            int x0, x1, y0, y1, z0, z1;
+            range(i, 0, &x0, &x1);
+            range(i, 1, &y0, &y1);
+            range(i, 2, &z0, &z1);
+            for (int z = z0; z <= z1; ++z)
+                for (int y = y0; y <= y1; ++y)
+                    for (int x = x0; x <= x1; ++x) {
+                        const size_t c = (size_t)x + (size_t)nd[0] * ((size_t)y + (size_t)nd[1] * z);
+                        if (pass == 0) g.cell_start[c] += 1u;
+                        else g.items[fill[c]++] = i;
+                    }
+        }
+    }
+}
+
 int set_scene_locked(rtw_ctx* ctx, const float* geom4, const float* mat4, const uint32_t* kind, uint32_t n) {
     if (n > 0 && (!geom4 || !mat4 || !kind)) return fail(ctx, RTW_E_INVALID_ARG, "scene arrays are NULL");
     if (n > (1u << 26)) return fail(ctx, RTW_E_INVALID_ARG, "too many spheres");
@@ -369,6 +481,23 @@ int set_scene_locked(rtw_ctx* ctx, const float* geom4, const float* mat4, const 
                 std::memcpy(perm[v].data() + ((size_t)(c * coop + h) * 32u + j) * 4u, geom4 + 4 * (size_t)kl, 16);
             }
         }
+    }
+    HostGrid hg;
+    build_grid(geom4, n, &hg);
+    ctx->grid = hg.hdr;
+    ctx->grid.n_big = (uint32_t)hg.big.size();
+    for (auto& ds : ctx->dev) {
+        RTW_CUDA(ctx, cudaSetDevice(ds.device));
+        int grc = grow(ctx, &ds.d_grid_start, &ds.grid_start_cap, hg.cell_start.size());
+        if (!grc) grc = grow(ctx, &ds.d_grid_items, &ds.grid_items_cap, hg.items.size());
+        if (!grc) grc = grow(ctx, &ds.d_grid_big, &ds.grid_big_cap, hg.big.size());
+        if (grc) return grc;
+        if (!hg.cell_start.empty())
+            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_grid_start, hg.cell_start.data(), hg.cell_start.size() * 4, cudaMemcpyHostToDevice, ds.stream));
+        if (!hg.items.empty())
+            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_grid_items, hg.items.data(), hg.items.size() * 4, cudaMemcpyHostToDevice, ds.stream));
+        if (!hg.big.empty())
+            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_grid_big, hg.big.data(), hg.big.size() * 4, cudaMemcpyHostToDevice, ds.stream));
     }
     for (auto& ds : ctx->dev) {
         RTW_CUDA(ctx, cudaSetDevice(ds.device));
@@ -803,6 +932,7 @@ int rtw_destroy(rtw_ctx* ctx) {
         cudaFree(ds.d_geom_perm[0]); cudaFree(ds.d_geom_perm[1]); cudaFree(ds.d_uv);
         cudaFree(ds.d_geom64); cudaFree(ds.d_mat64); cudaFree(ds.d_kind64);
         cudaFree(ds.d_tile64); cudaFree(ds.d_gather64); cudaFree(ds.d_image64);
+        cudaFree(ds.d_grid_start); cudaFree(ds.d_grid_items); cudaFree(ds.d_grid_big);
         cudaFree(ds.d_accum); cudaFree(ds.d_counters); cudaFree(ds.d_tile);
         cudaFree(ds.d_gather); cudaFree(ds.d_image); cudaFree(ds.d_rgb8); cudaFree(ds.d_scratch); cudaFree(ds.d_wf);
         if (ds.h_counters) cudaFreeHost(ds.h_counters);
@@ -822,7 +952,8 @@ int rtw_set_option(rtw_ctx* ctx, int option, int64_t value) {
     std::lock_guard<std::mutex> lock(ctx->mu);
     switch (option) {
         case RTW_OPT_MODE:
-            if (value != RTW_MODE_FUSED && value != RTW_MODE_WAVEFRONT && value != RTW_MODE_CTA_WAVEFRONT) return fail(ctx, RTW_E_INVALID_ARG, "unknown mode");
+            if (value != RTW_MODE_FUSED && value != RTW_MODE_WAVEFRONT && value != RTW_MODE_CTA_WAVEFRONT && value != RTW_MODE_GRID)
+                return fail(ctx, RTW_E_INVALID_ARG, "unknown mode");
             ctx->mode = (int)value;
             return RTW_OK;
         case RTW_OPT_STRIP:

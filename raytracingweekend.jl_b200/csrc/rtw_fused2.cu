@@ -21,6 +21,7 @@
 //     (one LEA + LDS.128 per candidate), keeps (t, position) only and decodes the list index once.
 #include "rtw_kernels.h"
 #include "rtw_sweep.cuh"
+#include "rtw_grid.cuh"
 
 namespace rtw {
 
@@ -365,7 +366,7 @@ __device__ __forceinline__ void merge_partial_hits(const float (&bt)[kCoop], con
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------
-template <bool kMulti, int kCoop, bool kOwnWalk>
+template <bool kMulti, int kCoop, bool kOwnWalk, bool kGrid = false>
 __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __grid_constant__ TraceParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_bar[2];
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
     const uint32_t n_stage = (n + 1u) & ~1u;
     const uint32_t n_tiles = kMulti ? (n + kTileSpheres - 1u) / kTileSpheres : 1u;
     constexpr uint32_t kGran = 32u * kCoop;
-    const uint32_t tile_cap = kMulti ? kTileSpheres : ((n + kGran - 1u) / kGran) * kGran;
+    const uint32_t tile_cap = kGrid ? 0u : (kMulti ? kTileSpheres : ((n + kGran - 1u) / kGran) * kGran);
     float4* s_tile0 = reinterpret_cast<float4*>(smem_raw);
     float4* s_tile1 = s_tile0 + tile_cap;  // kMulti: second streaming buffer; else: permuted AoS copy of the list
     uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tile0 + 2u * tile_cap) + threadIdx.x;
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     uint32_t bar_phase0 = 0u, bar_phase1 = 0u;
-    if (!kMulti) {
+    if (!kMulti && !kGrid) {
         if (threadIdx.x == 0 && n > 0u) {
             mbar_arrive_expect_tx(&s_bar[0], n_stage * 16u + tile_cap * 16u);
             tma_bulk_g2s(s_tile0, g_src, n_stage * 16u, &s_bar[0]);
@@ -631,7 +632,9 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
         // ------------------------------------------------------------ intersect: closest hit over the list
         best_t = __int_as_float(0x7f800000);  // typemax(T) = Inf, src/ray_color.jl:19
         best_k = -1;
-        {
+        if (kGrid) {
+            closest_hit_grid(P.grid, P.geom, o, d, alive, best_t, best_k);
+        } else {
             const uint32_t h = threadIdx.x & (kCoop - 1);
             f3 so[kCoop], sd[kCoop];
             bool sa[kCoop];
@@ -745,6 +748,32 @@ cudaError_t launch_uv_tables(int W, int H, float* u_tab, float* v_tab, cudaStrea
     const int n = W > H ? W : H;
     if (n <= 0) return cudaSuccess;
     uv_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(W, H, u_tab, v_tab);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fused_trace2_grid(const TraceParams& p, int num_sms, int blocks_per_sm_override, cudaStream_t stream,
+                                     LaunchInfo* info) {
+    auto kern = fused_trace2_kernel<false, 2, false, true>;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTraceBlock, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    if (blocks_per_sm_override > 0 && blocks_per_sm_override < per_sm) per_sm = blocks_per_sm_override;
+    long long grid = (long long)num_sms * per_sm;
+    const long long max_useful = (long long)((p.n_paths + (unsigned long long)kTraceBlock - 1ull) /
+                                             (unsigned long long)kTraceBlock);
+    if (grid > max_useful) grid = max_useful;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, kTraceBlock, 0, stream>>>(p);
+    if (info) {
+        info->grid = (int)grid;
+        info->block = kTraceBlock;
+        info->smem_bytes = 0;
+        info->blocks_per_sm = per_sm;
+        info->launches = 1;
+        info->rays_per_lane = 1;
+        info->sweep = 0;
+    }
     return cudaGetLastError();
 }
 

@@ -18,6 +18,17 @@ struct MagicDiv {
     uint32_t m, sh1, sh2;
 };
 
+// RTW_MODE_GRID: uniform grid over the small spheres + list of big ones (rtw_grid.cuh); nx == 0: no grid
+struct GridParams {
+    float ox, oy, oz;  // minimum corner
+    float h, inv_h;    // cell edge
+    int nx, ny, nz;
+    const uint32_t* cell_start;  // nx*ny*nz + 1 offsets into items
+    const uint32_t* items;       // sphere indices per cell, ascending
+    const uint32_t* big;         // spheres every ray tests
+    uint32_t n_big;
+};
+
 struct TraceParams {
     DevCamera cam;
     const float4* geom;
@@ -30,6 +41,7 @@ struct TraceParams {
     const float* v_tab;  // H entries: T((H-1-i0)/H), src/render.jl:27
     MagicDiv div_spp, div_w;
     uint32_t rk[20];  // Philox round keys: rk[2r] = key0 + r*W0, rk[2r+1] = key1 + r*W1
+    GridParams grid;  // RTW_MODE_GRID only
     const float4* mat;
     const uint32_t* kind;
     uint32_t n_spheres;
@@ -99,6 +111,9 @@ cudaError_t launch_fused_trace(const TraceParams& p, int num_sms, int blocks_per
 // walk: 1 = per-slot walks + merge, 2 = every lane resolves the candidates of its own ray (transposed), 0 = default
 cudaError_t launch_fused_trace2(const TraceParams& p, int num_sms, int blocks_per_sm_override, int coop, int walk,
                                 cudaStream_t stream, LaunchInfo* info);
+// RTW_MODE_GRID: the unified-tail kernel with the grid traversal in place of the sweep (needs TraceParams.grid)
+cudaError_t launch_fused_trace2_grid(const TraceParams& p, int num_sms, int blocks_per_sm_override, cudaStream_t stream,
+                                     LaunchInfo* info);
 cudaError_t launch_uv_tables(int W, int H, float* u_tab, float* v_tab, cudaStream_t stream);
 MagicDiv make_magic_div(uint32_t d);
 // RTW_MODE_WAVEFRONT (rtw_wavefront.cu); synchronises `stream` internally (host-driven step loop)

@@ -58,7 +58,7 @@ def test_option_and_error_constants_match_header(rtw):
     for name in ("RTW_OK", "RTW_E_INVALID_ARG", "RTW_E_NO_DEVICE", "RTW_E_NO_SCENE", "RTW_E_UNSUPPORTED",
                  "RTW_E_INTERNAL", "RTW_OPT_MODE", "RTW_OPT_STRIP", "RTW_OPT_BLOCKS_PER_SM", "RTW_OPT_COLLECT_TIMING",
                  "RTW_OPT_RAYS_PER_LANE", "RTW_OPT_SWEEP", "RTW_OPT_COOP", "RTW_OPT_TAIL", "RTW_OPT_WALK", "RTW_WALK_DEFAULT", "RTW_WALK_SLOTS", "RTW_WALK_OWN_RAY", "RTW_TAIL_DEFAULT", "RTW_TAIL_SPLIT",
-                 "RTW_TAIL_UNIFIED", "RTW_MODE_FUSED", "RTW_MODE_WAVEFRONT", "RTW_MODE_CTA_WAVEFRONT"):
+                 "RTW_TAIL_UNIFIED", "RTW_MODE_FUSED", "RTW_MODE_WAVEFRONT", "RTW_MODE_CTA_WAVEFRONT", "RTW_MODE_GRID"):
         m = re.search(rf"#define\s+{name}\s+\(?(-?\d+)\)?", text)
         assert m, name
         assert int(m.group(1)) == getattr(rtw._lib, name), name

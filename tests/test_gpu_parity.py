@@ -530,3 +530,60 @@ def test_float64_golden_fixture(rtw, renderer):
     img = renderer.render(rtw.t_default_cam(np.float64), 96, 16, max_depth=16, seed=1, scene=scene)
     assert float(np.abs(img - gold["image"]).max()) <= F64_TOL
     assert renderer.last_stats["ray_segments"] == int(gold["ray_segments"])
+
+
+def test_grid_mode_same_bits_as_the_linear_sweep(rtw, oracle, renderer, scenes):
+    # RTW_MODE_GRID tests far fewer spheres per ray but must return the same closest hit: identical images and
+    # ray-segment counts on every reference scene, on coincident spheres (ties), on ragged sub-lists, on lists where
+    # everything is "big" and on a camera inside the sphere field
+    tie_geom = np.array([[0, 0, -1, 0.5]] * 7 + [[0, -100.5, -1, 100]] + [[0.3 * i - 3, 0.1, -2 - 0.2 * i, 0.1] for i in range(20)],
+                        np.float32)
+    tie_mat = np.tile(np.array([[0.2, 0.9, 0.4, 0]], np.float32), (len(tie_geom), 1))
+    tie_mat[:7, :3] = [[1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 0], [0, 1, 1], [1, 0, 1], [0.2, 0.9, 0.4]]
+    tie = (tie_geom, tie_mat, np.zeros(len(tie_geom), np.uint32))
+    g, m, k = scenes["random"]
+    inside_cam = rtw.default_camera([2.3, 0.25, 1.1], [0, 0.3, 0], [0, 1, 0], 70, 16 / 9, 0.05, 2.0)
+    cases = [(scenes["two"], rtw.t_default_cam(), 96, 16, 4, 1), (scenes["four"], rtw.t_default_cam(), 96, 8, 16, 2),
+             (scenes["diel"], rtw.t_cam2(), 128, 16, 16, 3), (scenes["bubble"], rtw.t_default_cam(), 96, 8, 50, 4),
+             (scenes["bluered"], rtw.t_default_cam(), 64, 8, 8, 5), ((g, m, k), rtw.t_cam1(), 240, 16, 50, 6),
+             ((g, m, k), inside_cam, 160, 8, 30, 7), (tie, rtw.t_default_cam(), 96, 8, 8, 8)]
+    for n in (9, 33, 130, 257):
+        order = np.concatenate([[0], np.arange(len(k) - 3, len(k)), np.arange(1, len(k) - 3)])[:n]
+        cases.append(((g[order].copy(), m[order].copy(), k[order].copy()), rtw.t_cam1(), 64, 4, 12, 11))
+    renderer.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_GRID)
+    try:
+        for scene, cam, W, spp, depth, seed in cases:
+            img = renderer.render(cam, W, spp, max_depth=depth, seed=seed, scene=scene)
+            segs = renderer.last_stats["ray_segments"]
+            ref, _, ost = oracle.render(*scene, cam.as_array(), W, spp, max_depth=depth, seed=seed)
+            _compare(img, ref)
+            assert segs == ost["ray_segments"], (len(scene[2]), seed)
+        empty = (np.zeros((0, 4), np.float32), np.zeros((0, 4), np.float32), np.zeros(0, np.uint32))
+        img = renderer.render(rtw.t_default_cam(), 64, 2, scene=empty)
+        ref, _, _ = oracle.render(*empty, rtw.t_default_cam().as_array(), 64, 2)
+        _compare(img, ref)
+    finally:
+        renderer.set_option(rtw.RTW_OPT_MODE, 0)
+
+
+def test_grid_mode_100k_spheres_and_full_size(rtw, oracle, renderer, scenes):
+    rtw.reseed()
+    scene = rtw.flatten_scene(rtw.scene_random_spheres(half_extent=158))
+    cam = rtw.t_cam1()
+    renderer.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_GRID)
+    try:
+        img = renderer.render(cam, 48, 2, max_depth=8, scene=scene)
+        segs = renderer.last_stats["ray_segments"]
+        ref, _, ost = oracle.render(*scene, cam.as_array(), 48, 2, max_depth=8)
+        _compare(img, ref)
+        assert segs == ost["ray_segments"]
+        # full resolution, both modes on the GPU: the grid image is the linear-sweep image, bit for bit
+        a = np.array(renderer.render(cam, 1920, 4, max_depth=50, seed=3, scene=scenes["random"]))
+        sa = dict(renderer.last_stats)
+        renderer.set_option(rtw.RTW_OPT_MODE, 0)
+        b = np.array(renderer.render(cam, 1920, 4, max_depth=50, seed=3, scene=scenes["random"]))
+        sb = dict(renderer.last_stats)
+        assert np.array_equal(a, b) and sa["ray_segments"] == sb["ray_segments"]
+        print(f"grid {sa['ms_trace']:.2f} ms vs linear sweep {sb['ms_trace']:.2f} ms at 1920x1080x4spp")
+    finally:
+        renderer.set_option(rtw.RTW_OPT_MODE, 0)

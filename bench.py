@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--half-extent", type=int, default=11,
                     help="grid half extent of scene_random_spheres: 11 = the reference scene (484 spheres), "
                          "158 = BASELINE configs[4] (~100k spheres, TMA-streamed sweep)")
+    ap.add_argument("--mode", default="linear", choices=["linear", "grid"],
+                    help="linear = the sphere-list sweep of the reference (default, the benchmarked path); grid = "
+                         "RTW_MODE_GRID, the same image from a uniform-grid traversal (not comparable with the roofline)")
     return ap.parse_args()
 
 
@@ -200,6 +203,8 @@ def run_ours(args):
     rows_pad = R.sharding.rows_pad(H, G)
 
     r = R.Renderer([local_rank])
+    if args.mode == "grid":
+        r.set_option(R.RTW_OPT_MODE, R.RTW_MODE_GRID)
     r.set_scene(scene)
     # a dedicated (non-default) stream: the library enqueues on exactly this stream, so torch CUDA events see it
     stream = torch.cuda.Stream(dev)
@@ -347,6 +352,13 @@ def run_ours(args):
             },
             "clocks": clocks,
         }
+        if args.mode == "grid":
+            # the grid traversal skips most ray-sphere tests: the linear-sweep work model does not apply
+            line["mode"] = "grid (RTW_MODE_GRID: uniform-grid traversal, same image bits as the linear sweep)"
+            line["config"]["kernel"] = "fused persistent trace, unified tail, uniform-grid closest hit + resolve"
+            line["roofline"] = {"bound": "latency/divergence (per-lane grid traversal); no linear-sweep work model",
+                                "achieved": None, "peak": fp32_peak / 1e12, "unit": "T FP32 instr/s", "frac": None,
+                                "equivalent_linear_sweep_T_instr_s": achieved_instr, "traffic": None}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

@@ -408,7 +408,10 @@ void build_grid(const float* geom4, uint32_t n, HostGrid* out) {
     };
     int nd[3];
     while (dims(h, nd) > 2.0 * (double)small.size() + 64.0 || nd[0] > 1024 || nd[1] > 1024 || nd[2] > 1024) h *= 1.25;
-    const double inflate = 1e-3 * h;
+    const double inflate = 0.05 * h;  // registration margin: rounding of the traversal AND the reference's a = 1 shortcut
+    double r_min = 1e300;
+    for (uint32_t i : small) r_min = std::min(r_min, (double)radii[i]);
+    g.hdr.safe2 = (float)(0.5 * ((r_min + inflate) * (r_min + inflate) - r_min * r_min));  // half of it: slack for rounding
     g.hdr.h = (float)h;
     g.hdr.inv_h = 1.0f / g.hdr.h;
     g.hdr.ox = (float)(lo[0] - 0.5 * h);

@@ -633,7 +633,10 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
         best_t = __int_as_float(0x7f800000);  // typemax(T) = Inf, src/ray_color.jl:19
         best_k = -1;
         if (kGrid) {
-            closest_hit_grid(P.grid, P.geom, o, d, alive, best_t, best_k);
+            const bool unsafe = closest_hit_grid(P.grid, P.geom, o, d, alive, n <= kGridFallbackMax, best_t, best_k);
+            // rays the grid cannot answer exactly (non-unit direction after a glass reflection, very long flights):
+            // warp-cooperative sweep of the whole list; for lists > kGridFallbackMax the grid answer stands
+            if (n <= kGridFallbackMax) grid_fallback_sweep(P.geom, n, o, d, unsafe, best_t, best_k);
         } else {
             const uint32_t h = threadIdx.x & (kCoop - 1);
             f3 so[kCoop], sd[kCoop];

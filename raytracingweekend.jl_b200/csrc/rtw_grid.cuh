@@ -9,10 +9,20 @@
 //
 // Structure (built on the host, csrc/rtw_capi.cu build_grid): spheres much larger than the typical one ("big":
 // |r| > 4 x median, e.g. the r = 1000 ground) are kept in a list that every ray tests; the others are binned into a
-// uniform grid over their bounding box by their AABB inflated by 1e-3 cell edges, so a sphere is registered in
+// uniform grid over their bounding box by their AABB inflated by 5 % of a cell edge, so a sphere is registered in
 // every cell its surface can reach, with slack far above the rounding of the traversal.  A ray walks the cells it
 // crosses front to back (3-D DDA) and stops as soon as the closest hit so far lies before the exit of the current
 // cell: any sphere registered only in later cells is at least the inflation margin beyond that exit.
+//
+// One subtlety makes "the same closest hit" more than geometry.  hit(::Sphere) assumes a unit direction (a = 1,
+// src/hit.jl:14-15), but scatter(::Dielectric) returns reflect(...) un-normalised (src/material.jl:48) and in Float32
+// the normal (p - c)/r of a small far sphere is off by up to ~1e-4, so |d|^2 = 1 + eps with eps up to ~1e-3 after a
+// glass reflection (and ~3e-7 by plain rounding otherwise).  With a = 1 + eps the reference's discriminant
+// hb^2 - c accepts spheres whose distance rho from the ray line satisfies rho^2 <= r^2 + eps*m^2 (m = distance along
+// the ray): far spheres grow.  The linear sweep reproduces that arithmetic by construction; the grid only sees
+// spheres near the geometric ray.  So the traversal is used only while eps*t_exit^2 stays below what the
+// registration margin covers ((r_min + inflate)^2 - r_min^2, GridParams::safe2); a ray beyond that is reported as
+// unsafe and the caller resolves it by a warp-cooperative sweep of the whole list (lists <= kGridFallbackMax).
 #pragma once
 #include "rtw_kernels.h"
 
@@ -37,10 +47,16 @@ __device__ __forceinline__ void grid_test_sphere(const float4 s, uint32_t k, con
     }
 }
 
-__device__ __forceinline__ void closest_hit_grid(const GridParams& G, const float4* __restrict__ geom, const f3 o,
-                                                 const f3 d, const bool alive, float& best_t, int& best_k) {
+constexpr uint32_t kGridFallbackMax = 4096;  // lists up to this size resolve unsafe rays exactly (cooperative sweep)
+
+// returns true when the ray is "unsafe" for the grid (see above) and can_fallback is set: the result is then NOT
+// final and the caller must run grid_fallback_sweep; without can_fallback the grid answer is returned regardless
+__device__ __forceinline__ bool closest_hit_grid(const GridParams& G, const float4* __restrict__ geom, const f3 o,
+                                                 const f3 d, const bool alive, const bool can_fallback, float& best_t,
+                                                 int& best_k) {
     float bt = __int_as_float(0x7f800000);  // typemax(T) = Inf, src/ray_color.jl:19
     int bk = -1;
+    bool unsafe = false;
     if (alive) {
         for (uint32_t i = 0; i < G.n_big; ++i) {
             const uint32_t k = __ldg(G.big + i);
@@ -57,7 +73,21 @@ __device__ __forceinline__ void closest_hit_grid(const GridParams& G, const floa
             float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
             const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
             // enter a little early / accept a little late: the cells are clamped, so slack only costs a cell
-            if (t0 <= t1 * 1.0001f + 1e-4f && t0 < bt) {
+            // |d|^2 - 1, with a floor for the rounding of a normalised Float32 vector
+            const float eps = fmaxf(fabsf(fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x)) - 1.0f), 4e-7f);
+            const bool enters = t0 <= t1 * 1.0001f + 1e-4f && t0 < bt;
+            // how far along the ray a grid sphere can matter: the exit of the box, or -- for a ray that misses the box
+            // with a visibly non-unit direction -- the far side of the box's bounding ball; never beyond the closest
+            // big-sphere hit
+            float t_far = t1;
+            if (!enters) {
+                const float mx = G.ox + 0.5f * hx - o.x, my = G.oy + 0.5f * hy - o.y, mz = G.oz + 0.5f * hz - o.z;
+                t_far = eps > 1e-6f ? sqrtf(mx * mx + my * my + mz * mz) + 0.5f * sqrtf(hx * hx + hy * hy + hz * hz) : 0.0f;
+            }
+            t_far = fminf(t_far, bt);
+            if (can_fallback && eps * t_far * t_far > G.safe2) {
+                unsafe = true;
+            } else if (enters) {
                 const float px = fmaf(t0, d.x, o.x), py = fmaf(t0, d.y, o.y), pz = fmaf(t0, d.z, o.z);
                 int cx = min(max((int)floorf((px - G.ox) * G.inv_h), 0), G.nx - 1);
                 int cy = min(max((int)floorf((py - G.oy) * G.inv_h), 0), G.ny - 1);
@@ -79,7 +109,7 @@ __device__ __forceinline__ void closest_hit_grid(const GridParams& G, const floa
                         grid_test_sphere(__ldg(geom + k), k, o, d, bt, bk);
                     }
                     const float texit = fminf(tx, fminf(ty, tz));
-                    if (bt < texit) break;  // nothing registered only in later cells can be closer (inflation margin)
+                    if (bt < texit) break;  // nothing registered only in later cells can be closer (registration margin)
                     if (tx <= ty && tx <= tz) {
                         cx += sx;
                         if ((unsigned)cx >= (unsigned)G.nx) break;
@@ -99,6 +129,37 @@ __device__ __forceinline__ void closest_hit_grid(const GridParams& G, const floa
     }
     best_t = bt;
     best_k = bk;
+    return unsafe;
+}
+
+// Exact closest hit for the unsafe rays of a warp: one ray at a time, the 32 lanes split the list, the partial
+// results are reduced with the tie rule (equal t: larger index).  Called by all lanes of the warp.
+__device__ __forceinline__ void grid_fallback_sweep(const float4* __restrict__ geom, uint32_t n, const f3 o, const f3 d,
+                                                    bool unsafe, float& best_t, int& best_k) {
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned pending = __ballot_sync(0xffffffffu, unsafe);
+    while (pending) {
+        const int src = __ffs((int)pending) - 1;
+        pending &= pending - 1u;
+        const f3 ro = mk3(__shfl_sync(0xffffffffu, o.x, src), __shfl_sync(0xffffffffu, o.y, src), __shfl_sync(0xffffffffu, o.z, src));
+        const f3 rd = mk3(__shfl_sync(0xffffffffu, d.x, src), __shfl_sync(0xffffffffu, d.y, src), __shfl_sync(0xffffffffu, d.z, src));
+        float bt = __int_as_float(0x7f800000);
+        int bk = -1;
+        for (uint32_t k = lane; k < n; k += 32u) grid_test_sphere(__ldg(geom + k), k, ro, rd, bt, bk);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float pt = __shfl_xor_sync(0xffffffffu, bt, off);
+            const int pk = __shfl_xor_sync(0xffffffffu, bk, off);
+            if (pk >= 0 && (bk < 0 || pt < bt || (pt == bt && pk > bk))) {
+                bt = pt;
+                bk = pk;
+            }
+        }
+        if ((int)lane == src) {
+            best_t = bt;
+            best_k = bk;
+        }
+    }
 }
 
 }  // namespace

@@ -22,6 +22,7 @@ struct MagicDiv {
 struct GridParams {
     float ox, oy, oz;  // minimum corner
     float h, inv_h;    // cell edge
+    float safe2;       // (r_min + inflate)^2 - r_min^2: the growth of r^2 the registration margin covers (rtw_grid.cuh)
     int nx, ny, nz;
     const uint32_t* cell_start;  // nx*ny*nz + 1 offsets into items
     const uint32_t* items;       // sphere indices per cell, ascending

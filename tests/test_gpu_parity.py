@@ -587,3 +587,45 @@ def test_grid_mode_100k_spheres_and_full_size(rtw, oracle, renderer, scenes):
         print(f"grid {sa['ms_trace']:.2f} ms vs linear sweep {sb['ms_trace']:.2f} ms at 1920x1080x4spp")
     finally:
         renderer.set_option(rtw.RTW_OPT_MODE, 0)
+
+
+def test_grid_mode_random_sphere_soups(rtw, renderer):
+    # adversarial lists for the grid: mixed radii over two decades (big/small classification), overlapping and nested
+    # spheres, negative radii, all three materials, 3-D clouds and flat layers, cameras inside the cloud and rays with
+    # exactly zero direction components (axis-aligned view, no lens).  Linear sweep vs grid, both on the GPU.
+    rng = np.random.default_rng(77)
+    for trial in range(24):
+        n = int(rng.choice([9, 17, 60, 200, 700, 1500]))
+        flat = trial % 3 == 0
+        centers = rng.uniform(-6, 6, size=(n, 3)).astype(np.float32)
+        if flat:
+            centers[:, 1] = rng.uniform(0.0, 0.3, size=n)
+        radii = (10.0 ** rng.uniform(-1.3, 0.2, size=n)).astype(np.float32) * (0.25 if n > 500 else 1.0)
+        radii[rng.random(n) < 0.05] *= -1.0  # hollow shells
+        if trial % 4 == 1:
+            radii[0] = 400.0  # a ground-like giant
+            centers[0] = [0, -400.5, 0]
+        geom = np.concatenate([centers, radii[:, None]], axis=1).astype(np.float32)
+        kind = rng.integers(0, 3, size=n).astype(np.uint32)
+        mat = rng.uniform(0.2, 1.0, size=(n, 4)).astype(np.float32)
+        mat[kind == 1, 3] = rng.uniform(0, 1.5, size=int((kind == 1).sum()))
+        mat[kind == 2, 3] = 1.5
+        mat[kind == 2, :3] = 1.0
+        mat[kind == 0, 3] = 0.0
+        scene = (geom, mat, kind)
+        if trial % 2 == 0:
+            cam = rtw.default_camera([0, 0.2, 9], [0, 0.2, 0], [0, 1, 0], 60, 16 / 9, 0.0, 1.0)  # axis-aligned view
+        else:
+            eye = rng.uniform(-3, 3, size=3)
+            cam = rtw.default_camera(list(eye), [0, 0, 0], [0, 1, 0], 75, 16 / 9, 0.1, 3.0)       # inside the cloud
+        renderer.set_scene(scene)
+        renderer.set_option(rtw.RTW_OPT_MODE, 0)
+        a = np.array(renderer.render(cam, 96, 4, max_depth=12, seed=trial))
+        sa = renderer.last_stats["ray_segments"]
+        renderer.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_GRID)
+        try:
+            b = np.array(renderer.render(cam, 96, 4, max_depth=12, seed=trial))
+            sb = renderer.last_stats["ray_segments"]
+        finally:
+            renderer.set_option(rtw.RTW_OPT_MODE, 0)
+        assert sa == sb and np.array_equal(a, b, equal_nan=True), (trial, n, flat, sa, sb, int((a != b).sum()))

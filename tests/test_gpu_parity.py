@@ -629,3 +629,47 @@ def test_grid_mode_random_sphere_soups(rtw, renderer):
         finally:
             renderer.set_option(rtw.RTW_OPT_MODE, 0)
         assert sa == sb and np.array_equal(a, b, equal_nan=True), (trial, n, flat, sa, sb, int((a != b).sum()))
+
+
+def _random_soup(rtw, rng, trial):
+    n = int(rng.choice([9, 17, 60, 200, 700, 1500]))
+    centers = rng.uniform(-6, 6, size=(n, 3)).astype(np.float32)
+    if trial % 3 == 0:
+        centers[:, 1] = rng.uniform(0.0, 0.3, size=n)
+    radii = (10.0 ** rng.uniform(-1.3, 0.2, size=n)).astype(np.float32) * (0.25 if n > 500 else 1.0)
+    radii[rng.random(n) < 0.05] *= -1.0
+    if trial % 4 == 1:
+        radii[0], centers[0] = 400.0, [0, -400.5, 0]
+    geom = np.concatenate([centers, radii[:, None]], axis=1).astype(np.float32)
+    kind = rng.integers(0, 3, size=n).astype(np.uint32)
+    mat = rng.uniform(0.2, 1.0, size=(n, 4)).astype(np.float32)
+    mat[kind == 1, 3] = rng.uniform(0, 1.5, size=int((kind == 1).sum()))
+    mat[kind == 2] = [1.0, 1.0, 1.0, 1.5]
+    mat[kind == 0, 3] = 0.0
+    if trial % 2 == 0:
+        cam = rtw.default_camera([0, 0.2, 9], [0, 0.2, 0], [0, 1, 0], 60, 16 / 9, 0.0, 1.0)
+    else:
+        cam = rtw.default_camera(list(rng.uniform(-3, 3, size=3)), [0, 0, 0], [0, 1, 0], 75, 16 / 9, 0.1, 3.0)
+    return (geom, mat, kind), cam
+
+
+@pytest.mark.parametrize("coop,tail,walk,mode", [(2, 2, 1, 0), (2, 2, 2, 0), (4, 2, 2, 0), (2, 1, 0, 0), (2, 0, 0, 2), (2, 0, 0, 3)])
+def test_random_sphere_soups_against_the_oracle(rtw, oracle, renderer, coop, tail, walk, mode):
+    # the adversarial lists of the grid test (tiny / nested / hollow spheres, glass-heavy, axis-aligned rays, cameras
+    # inside the cloud) through the kernel families, against the CPU oracle: same paths, segment for segment
+    rng = np.random.default_rng(1234)
+    for opt, v in ((rtw.RTW_OPT_COOP, coop), (rtw.RTW_OPT_TAIL, tail), (rtw.RTW_OPT_WALK, walk), (rtw.RTW_OPT_MODE, mode)):
+        renderer.set_option(opt, v)
+    try:
+        for trial in range(10):
+            scene, cam = _random_soup(rtw, rng, trial)
+            if mode == 2 and len(scene[2]) > 1024:
+                continue  # the CTA wavefront keeps the list in one tile
+            img = renderer.render(cam, 64, 4, max_depth=12, seed=trial, scene=scene)
+            segs = renderer.last_stats["ray_segments"]
+            ref, _, ost = oracle.render(*scene, cam.as_array(), 64, 4, max_depth=12, seed=trial)
+            assert segs == ost["ray_segments"], (trial, len(scene[2]))
+            _compare(img, ref)
+    finally:
+        for opt in (rtw.RTW_OPT_COOP, rtw.RTW_OPT_TAIL, rtw.RTW_OPT_WALK, rtw.RTW_OPT_MODE):
+            renderer.set_option(opt, 0)

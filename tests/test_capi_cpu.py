@@ -40,8 +40,10 @@ def test_abi_version_and_image_height(rtw):
 
 
 def test_struct_layouts_match_header_and_julia(rtw):
-    # Camera{Float32}: 7 x Vec3 + lens_radius = 22 floats = 88 bytes, src/camera.jl:1-10
+    # Camera{Float32}: 7 x Vec3 + lens_radius = 22 floats = 88 bytes, src/camera.jl:1-10; Camera{Float64}: 22 doubles
     assert C.sizeof(rtw.rtw_camera) == 88
+    assert C.sizeof(rtw._lib.rtw_camera_f64) == 176
+    assert [n for n, _ in rtw._lib.rtw_camera_f64._fields_] == [n for n, _ in rtw.rtw_camera._fields_]
     assert [n for n, _ in rtw.rtw_camera._fields_] == ["origin", "lower_left_corner", "horizontal", "vertical", "u", "v",
                                                        "w", "lens_radius"]
     text = HEADER.read_text()

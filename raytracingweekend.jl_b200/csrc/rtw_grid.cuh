@@ -21,8 +21,9 @@
 // hb^2 - c accepts spheres whose distance rho from the ray line satisfies rho^2 <= r^2 + eps*m^2 (m = distance along
 // the ray): far spheres grow.  The linear sweep reproduces that arithmetic by construction; the grid only sees
 // spheres near the geometric ray.  So the traversal is used only while eps*t_exit^2 stays below what the
-// registration margin covers ((r_min + inflate)^2 - r_min^2, GridParams::safe2); a ray beyond that is reported as
-// unsafe and the caller resolves it by a warp-cooperative sweep of the whole list (lists <= kGridFallbackMax).
+// registration margin covers ((r_min + inflate)^2 - r_min^2, GridParams::safe2), where t_exit is the closest hit
+// the traversal found (no unseen sphere beyond it can win) or the exit of the grid; a ray beyond that is reported
+// as unsafe and the caller resolves it by a warp-cooperative sweep of the whole list (lists <= kGridFallbackMax).
 #pragma once
 #include "rtw_kernels.h"
 
@@ -76,18 +77,7 @@ __device__ __forceinline__ bool closest_hit_grid(const GridParams& G, const floa
             // |d|^2 - 1, with a floor for the rounding of a normalised Float32 vector
             const float eps = fmaxf(fabsf(fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x)) - 1.0f), 4e-7f);
             const bool enters = t0 <= t1 * 1.0001f + 1e-4f && t0 < bt;
-            // how far along the ray a grid sphere can matter: the exit of the box, or -- for a ray that misses the box
-            // with a visibly non-unit direction -- the far side of the box's bounding ball; never beyond the closest
-            // big-sphere hit
-            float t_far = t1;
-            if (!enters) {
-                const float mx = G.ox + 0.5f * hx - o.x, my = G.oy + 0.5f * hy - o.y, mz = G.oz + 0.5f * hz - o.z;
-                t_far = eps > 1e-6f ? sqrtf(mx * mx + my * my + mz * mz) + 0.5f * sqrtf(hx * hx + hy * hy + hz * hz) : 0.0f;
-            }
-            t_far = fminf(t_far, bt);
-            if (can_fallback && eps * t_far * t_far > G.safe2) {
-                unsafe = true;
-            } else if (enters) {
+            if (enters) {
                 const float px = fmaf(t0, d.x, o.x), py = fmaf(t0, d.y, o.y), pz = fmaf(t0, d.z, o.z);
                 int cx = min(max((int)floorf((px - G.ox) * G.inv_h), 0), G.nx - 1);
                 int cy = min(max((int)floorf((py - G.oy) * G.inv_h), 0), G.ny - 1);
@@ -125,6 +115,17 @@ __device__ __forceinline__ bool closest_hit_grid(const GridParams& G, const floa
                     }
                 }
             }
+            // Safety of the answer (see the header): how far along the ray a sphere the traversal did not see could
+            // still matter -- up to the closest hit found (plus the reach of a small sphere), at most the exit of the
+            // box; for a ray that misses the box with a visibly non-unit direction, the far side of the box's
+            // bounding ball.
+            float t_far = t1;
+            if (!enters) {
+                const float mx = G.ox + 0.5f * hx - o.x, my = G.oy + 0.5f * hy - o.y, mz = G.oz + 0.5f * hz - o.z;
+                t_far = eps > 1e-6f ? sqrtf(mx * mx + my * my + mz * mz) + 0.5f * sqrtf(hx * hx + hy * hy + hz * hz) : 0.0f;
+            }
+            t_far = fminf(t_far, bt + 2.0f * G.h);
+            unsafe = can_fallback && eps * t_far * t_far > G.safe2;
         }
     }
     best_t = bt;

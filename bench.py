@@ -310,6 +310,22 @@ def run_ours(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.SUM)
     e2e_value = float(e2e_s.item()) / float(e2e_t.item()) / 1e6
 
+    # ---- extra (N = 1, default mode only): the same workload through RTW_MODE_GRID -- same image bits, reported beside
+    # the headline, never instead of it (the benchmarked path is the reference's linear sweep)
+    grid_extra = None
+    if world == 1 and args.mode == "linear":
+        try:
+            r.set_option(R.RTW_OPT_MODE, R.RTW_MODE_GRID)
+            one_step_resident()
+            g_ms, g_segs, _ = timed_steps(lambda: (one_step_resident(), None)[1], 2)
+            grid_extra = {"value": g_segs / (sum(g_ms) * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": sum(g_ms) / 2, "steps": 2,
+                          "note": "RTW_MODE_GRID: uniform-grid traversal instead of the linear sweep, bit-identical image; "
+                                  "not the benchmarked path (no linear-sweep roofline applies)"}
+        except Exception as e:  # the headline must not depend on the optional mode
+            grid_extra = {"error": str(e)}
+        finally:
+            r.set_option(R.RTW_OPT_MODE, R.RTW_MODE_FUSED)
+
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -359,6 +375,8 @@ def run_ours(args):
             line["roofline"] = {"bound": "latency/divergence (per-lane grid traversal); no linear-sweep work model",
                                 "achieved": None, "peak": fp32_peak / 1e12, "unit": "T FP32 instr/s", "frac": None,
                                 "equivalent_linear_sweep_T_instr_s": achieved_instr, "traffic": None}
+        if grid_extra is not None:
+            line["grid_mode"] = grid_extra
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

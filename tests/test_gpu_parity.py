@@ -673,3 +673,16 @@ def test_random_sphere_soups_against_the_oracle(rtw, oracle, renderer, coop, tai
     finally:
         for opt in (rtw.RTW_OPT_COOP, rtw.RTW_OPT_TAIL, rtw.RTW_OPT_WALK, rtw.RTW_OPT_MODE):
             renderer.set_option(opt, 0)
+
+
+def test_float64_path_on_random_soups(rtw, oracle, renderer):
+    rng = np.random.default_rng(4321)
+    for trial in range(8):
+        scene, cam32 = _random_soup(rtw, rng, trial)
+        scene = tuple(a.astype(np.float64) if a.dtype == np.float32 else a for a in scene)
+        cam = rtw.default_camera([0, 0.2, 9], [0, 0.2, 0], [0, 1, 0], 60, 16 / 9, 0.05 * (trial % 2), 9.0, elem_type=np.float64)
+        img = renderer.render(cam, 64, 4, max_depth=12, seed=trial, scene=scene)
+        segs = renderer.last_stats["ray_segments"]
+        ref, _, ost = oracle.render(*scene, cam.as_array(), 64, 4, max_depth=12, seed=trial, f64=True)
+        assert segs == ost["ray_segments"], (trial, len(scene[2]))
+        assert float(np.abs(img - ref).max()) <= F64_TOL

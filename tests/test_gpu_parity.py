@@ -686,3 +686,35 @@ def test_float64_path_on_random_soups(rtw, oracle, renderer):
         ref, _, ost = oracle.render(*scene, cam.as_array(), 64, 4, max_depth=12, seed=trial, f64=True)
         assert segs == ost["ray_segments"], (trial, len(scene[2]))
         assert float(np.abs(img - ref).max()) <= F64_TOL
+
+
+def test_progressive_and_float64_on_several_devices(rtw, scenes):
+    # rows interleaved over the devices of a context: progressive passes, the checkpoint (read on 2 devices, resumed
+    # on 1), the 8-bit image and the Float64 render all equal their single-device results.  Needs >= 2 GPUs.
+    import ctypes as C
+    n = C.c_int()
+    rtw._lib.load().rtw_device_count(C.byref(n))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs")
+    cam, W, total = rtw.t_cam1(), 200, 12
+    with rtw.Renderer([0]) as r1, rtw.Renderer([0, 1]) as r2:
+        r1.set_scene(scenes["random"])
+        r2.set_scene(scenes["random"])
+        full = np.array(r1.render(cam, W, total, max_depth=16, seed=5))
+        r2.accumulate(cam, W, 0, 5, total, max_depth=16, seed=5)
+        ckpt = r2.accumulator_read()
+        r2.accumulate(cam, W, 5, 7, total, max_depth=16, seed=5)
+        assert np.array_equal(np.array(r2.resolve()), full)
+        u8_two = r2.resolve_rgb8()
+        r1.accumulator_write(ckpt, W, 5, total)
+        r1.accumulate(cam, W, 5, 7, total, max_depth=16, seed=5)
+        assert np.array_equal(np.array(r1.resolve()), full)
+        assert np.array_equal(r1.resolve_rgb8(), u8_two)
+        cam64 = rtw.t_cam1(np.float64)
+        rtw.reseed()
+        s64 = rtw.flatten_scene(rtw.scene_random_spheres(elem_type=np.float64), np.float64)
+        a = np.array(r1.render(cam64, 160, 4, max_depth=16, scene=s64))
+        b = np.array(r2.render(cam64, 160, 4, max_depth=16, scene=s64))
+        assert np.array_equal(a, b)
+        r2.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_GRID)
+        assert np.array_equal(np.array(r2.render(cam, W, total, max_depth=16, seed=5, scene=scenes["random"])), full)

@@ -1,5 +1,10 @@
-import sys, numpy as np
-sys.path.insert(0, "/root/repo")
+"""Times the Float64 path on the headline scene.  Usage: python tools/f64_render.py [spp]"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import rtw_b200 as R
 R.reseed(); scene = R.flatten_scene(R.scene_random_spheres(elem_type=np.float64), np.float64)
 cam = R.t_cam1(np.float64)

@@ -1,7 +1,7 @@
 """The drop-in multi-GPU path a Julia user gets: ONE process, ONE rtw_render_scene call, rows interleaved over all
 devices of the context, tiles collected on device 0 by peer copies (no torch, no NCCL).  Times the headline workload
 end to end (host buffers in, host image out) for 1, 2, 4, 8 devices and checks the images are identical.
-Usage: python tools/multi_device_render.py [spp]   -> gpurun_out/multi_device_render.json"""
+Usage: python tools/multi_device_render.py [spp] [grid]   -> gpurun_out/multi_device_render[_grid].json"""
 import ctypes as C
 import json
 import sys
@@ -15,6 +15,7 @@ sys.path.insert(0, str(ROOT))
 import rtw_b200 as R  # noqa: E402
 
 spp = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+grid = len(sys.argv) > 2 and sys.argv[2] == "grid"
 n = C.c_int()
 R._lib.load().rtw_device_count(C.byref(n))
 R.reseed()
@@ -26,6 +27,8 @@ for g in (1, 2, 4, 8):
     if g > n.value:
         break
     with R.Renderer(list(range(g))) as r:
+        if grid:
+            r.set_option(R.RTW_OPT_MODE, R.RTW_MODE_GRID)
         r.render(cam, 1920, max(1, spp // 50), max_depth=50, scene=scene)  # warm-up: allocations, module load
         best = None
         for _ in range(3):
@@ -44,4 +47,5 @@ for g in (1, 2, 4, 8):
         out["runs"].append(rec)
         print(rec, flush=True)
 (ROOT / "gpurun_out").mkdir(exist_ok=True)
-(ROOT / "gpurun_out" / "multi_device_render.json").write_text(json.dumps(out, indent=1))
+out["mode"] = "RTW_MODE_GRID" if grid else "RTW_MODE_FUSED (linear sweep)"
+(ROOT / "gpurun_out" / ("multi_device_render_grid.json" if grid else "multi_device_render.json")).write_text(json.dumps(out, indent=1))

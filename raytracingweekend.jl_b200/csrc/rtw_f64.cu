@@ -54,7 +54,7 @@ __device__ __forceinline__ d3 unit_vector_d(const PathRng& g, uint32_t event, ui
 }
 
 template <bool kShared>
-__global__ void __launch_bounds__(kTraceBlock, 2) trace_f64_kernel(const __grid_constant__ TraceParams64 P) {
+__global__ void __launch_bounds__(kTraceBlock, 3) trace_f64_kernel(const __grid_constant__ TraceParams64 P) {
     extern __shared__ __align__(16) unsigned char smem_raw64[];
     double4* s_geom = reinterpret_cast<double4*>(smem_raw64);
     const uint32_t n = P.n_spheres;

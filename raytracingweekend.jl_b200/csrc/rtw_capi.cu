@@ -615,7 +615,7 @@ int pass_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int max_depth, uint6
         if (out_rgb)
             RTW_CUDA(ctx, cudaMemcpyAsync(out_rgb, d0.d_image, img_floats * sizeof(float), cudaMemcpyDeviceToHost, d0.stream));
         if (out_rgb8) {
-            // 8-bit image: reuse the gather buffer as scratch (W*H*3 bytes <= its size is not guaranteed: own buffer)
+            // 8-bit image: quantised on the device into its own buffer, then downloaded
             rc = grow(ctx, &d0.d_rgb8, &d0.rgb8_cap, img_floats);
             if (rc) return rc;
             RTW_CUDA(ctx, rtw::launch_quantize_rgb8(d0.d_image, W, H, d0.d_rgb8, d0.stream));

@@ -16,8 +16,8 @@ big = R.flatten_scene(R.scene_random_spheres(half_extent=17))  # > 1024 spheres:
 cam = R.t_cam1()
 with R.Renderer([0]) as r:
     for scene, W, spp in ((small, 64, 2), (big, 32, 1)):
-        for coop, tail, walk, mode in ((2, 2, 1, 0), (2, 2, 2, 0), (4, 2, 1, 0), (4, 2, 2, 0), (2, 1, 0, 0), (2, 0, 0, 2), (2, 0, 0, 1)):
-            if mode != 0 and len(scene[2]) > 1024:
+        for coop, tail, walk, mode in ((2, 2, 1, 0), (2, 2, 2, 0), (4, 2, 1, 0), (4, 2, 2, 0), (2, 1, 0, 0), (2, 0, 0, 2), (2, 0, 0, 1), (2, 0, 0, 3)):
+            if mode in (1, 2) and len(scene[2]) > 1024:
                 continue
             r.set_option(R.RTW_OPT_COOP, coop)
             r.set_option(R.RTW_OPT_TAIL, tail)

@@ -368,6 +368,13 @@ def run_ours(args):
             },
             "clocks": clocks,
         }
+        # secondary roofline: the kernel's measured DRAM traffic against the measured HBM copy bandwidth -- shows how far
+        # from HBM-bound this path is (the sphere list lives in shared memory, rays in registers)
+        traffic = line["roofline"]["traffic"]
+        hbm_peak, hbm_src = hbm_peak_gbs()
+        if traffic:
+            line["roofline"]["hbm"] = {"achieved": traffic / trace_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                       "frac": traffic / trace_s / 1e9 / hbm_peak, "peak_source": hbm_src}
         if args.mode == "grid":
             # the grid traversal skips most ray-sphere tests: the linear-sweep work model does not apply
             line["mode"] = "grid (RTW_MODE_GRID: uniform-grid traversal, same image bits as the linear sweep)"
@@ -383,6 +390,19 @@ def run_ours(args):
     r.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def hbm_peak_gbs():
+    """Measured HBM copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the profiling
+    recipe's stated fallback."""
+    try:
+        d = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        for key in ("hbm_gbs", "hbm_GBps", "hbm"):
+            if key in d:
+                return float(d[key]), "MEASURED_PEAKS.json (measured)"
+    except Exception:
+        pass
+    return 6650.0, "B200_PROFILING.md fallback (MEASURED_PEAKS.json absent)"
 
 
 def measured_dram_traffic():

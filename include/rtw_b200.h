@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RTW_ABI_VERSION 2
+#define RTW_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define RTW_API __attribute__((visibility("default")))
@@ -82,6 +82,11 @@ typedef struct rtw_stats {
     float ms_resolve;        /* accumulator -> gamma-2 RGB (src/render.jl:40, src/vec.jl:22)              */
     float ms_h2d;            /* scene / camera upload inside the call                                     */
     float ms_d2h;            /* image download inside the call                                            */
+    /* ABI v3 */
+    int32_t n_devices;       /* devices the call ran on (rows r -> device r mod n_devices)                 */
+    int32_t reserved0;
+    uint64_t grid_fallback_rays; /* RTW_MODE_GRID: ray segments the traversal could not answer exactly and that
+                                    were resolved by the exact whole-list sweep (0 in the other modes)         */
 } rtw_stats;
 
 typedef struct rtw_ctx rtw_ctx;
@@ -97,6 +102,12 @@ typedef struct rtw_ctx rtw_ctx;
 #define RTW_OPT_TAIL 8            /* RTW_TAIL_*: layout of the per-bounce work after the sweep (RTW_MODE_FUSED) */
 
 #define RTW_OPT_WALK 9            /* RTW_WALK_*: candidate resolution after the sweep (RTW_TAIL_UNIFIED, lists <= 1024) */
+
+#define RTW_OPT_GATHER 10         /* RTW_GATHER_*: how a multi-device context collects the row tiles on device 0 */
+
+#define RTW_GATHER_PEER 0         /* cudaMemcpyPeerAsync on each producer's stream (default; measured fastest)  */
+#define RTW_GATHER_NCCL 1         /* one grouped ncclSend/ncclRecv (single-process ncclCommInitAll); libnccl.so.2 is
+                                     bound with dlopen on first use -- RTW_E_UNSUPPORTED when it is not installed   */
 
 #define RTW_WALK_DEFAULT 0        /* library default (the fastest measured)                           */
 #define RTW_WALK_SLOTS 1          /* a lane resolves, slot by slot, the candidates it found; partial hits merged by shuffle */

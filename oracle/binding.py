@@ -12,6 +12,7 @@ import numpy as np
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "librtw_oracle.so"
+LIB_PATH_DEFAULT = LIB_PATH
 
 RNG_PHILOX = 0
 RNG_XOROSHIRO = 1
@@ -37,6 +38,14 @@ _lib = None
 
 def build() -> None:
     subprocess.run(["make", "-C", os.fspath(_HERE), "librtw_oracle.so"], check=True, capture_output=True)
+
+
+def use_library(path) -> None:
+    """Switch the binding to another build of the same source (bench.py: the -O3 -march=native timing build)."""
+    global _lib, LIB_PATH
+    LIB_PATH = Path(path)
+    _lib = None
+    load()
 
 
 def load() -> C.CDLL:

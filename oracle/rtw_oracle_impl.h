@@ -276,23 +276,25 @@ typedef struct {
     uint64_t segments, tests;
 } SFX(job);
 
-static void SFX(render_row)(SFX(job)* jb, SFX(world)* w, rtwo_rng* g, int i0) {
+static void SFX(render_pixel)(SFX(job)* jb, SFX(world)* w, rtwo_rng* g, int i0, int j0) {
     const int W = jb->W, H = jb->H;
-    for (int j0 = 0; j0 < W; ++j0) { /* :24 */
-        double acc[3] = {0.0, 0.0, 0.0}; /* :25 (promoted to Float64 by the first +=) */
-        for (int s0 = 0; s0 < jb->spp; ++s0) { /* :29 */
-            double rgb[3];
-            if (jb->rng_mode == RTWO_RNG_PHILOX) rtwo_rng_begin_path(g, jb->seed, (uint32_t)(i0 * W + j0), (uint32_t)s0);
-            SFX(sample_path)(w, g, &jb->cam, W, H, jb->max_depth, i0 + 1, j0 + 1, s0 + 1, rgb);
-            acc[0] += rgb[0]; acc[1] += rgb[1]; acc[2] += rgb[2]; /* :38 */
-        }
-        size_t at = ((size_t)j0 * (size_t)H + (size_t)i0) * 3; /* Julia column-major img[i,j] */
-        for (int k = 0; k < 3; ++k) {
-            double lin = acc[k] / (double)jb->spp;      /* :40 accum_color / n_samples */
-            if (jb->out_linear) jb->out_linear[at + k] = lin;
-            jb->out_rgb[at + k] = (RT)sqrt(lin);        /* rgb_gamma2, src/vec.jl:22; store rounds to T */
-        }
+    double acc[3] = {0.0, 0.0, 0.0}; /* :25 (promoted to Float64 by the first +=) */
+    for (int s0 = 0; s0 < jb->spp; ++s0) { /* :29 */
+        double rgb[3];
+        if (jb->rng_mode == RTWO_RNG_PHILOX) rtwo_rng_begin_path(g, jb->seed, (uint32_t)(i0 * W + j0), (uint32_t)s0);
+        SFX(sample_path)(w, g, &jb->cam, W, H, jb->max_depth, i0 + 1, j0 + 1, s0 + 1, rgb);
+        acc[0] += rgb[0]; acc[1] += rgb[1]; acc[2] += rgb[2]; /* :38 */
     }
+    size_t at = ((size_t)j0 * (size_t)H + (size_t)i0) * 3; /* Julia column-major img[i,j] */
+    for (int k = 0; k < 3; ++k) {
+        double lin = acc[k] / (double)jb->spp;      /* :40 accum_color / n_samples */
+        if (jb->out_linear) jb->out_linear[at + k] = lin;
+        jb->out_rgb[at + k] = (RT)sqrt(lin);        /* rgb_gamma2, src/vec.jl:22; store rounds to T */
+    }
+}
+
+static void SFX(render_row)(SFX(job)* jb, SFX(world)* w, rtwo_rng* g, int i0) {
+    for (int j0 = 0; j0 < jb->W; ++j0) SFX(render_pixel)(jb, w, g, i0, j0); /* :24 */
 }
 
 static void* SFX(worker)(void* arg) {
@@ -313,8 +315,14 @@ static void* SFX(worker)(void* arg) {
     } else {
         memset(&g, 0, sizeof g);
         g.mode = RTWO_RNG_PHILOX;
-        /* path-keyed stream: any row->thread map gives the same image; interleave for load balance */
-        for (int k = jb->tid; k < nrows; k += jb->nthreads) SFX(render_row)(jb, &w, &g, jb->row_start + k * jb->row_stride);
+        /* path-keyed stream: any pixel->thread map gives the same image; blocks of 16 pixels are dealt to the
+         * threads round-robin (load balance, and single-row slices of a wide image still use every core) */
+        const long total = (long)nrows * (long)jb->W;
+        for (long b = jb->tid; b * 16 < total; b += jb->nthreads) {
+            const long end = (b + 1) * 16 < total ? (b + 1) * 16 : total;
+            for (long p = b * 16; p < end; ++p)
+                SFX(render_pixel)(jb, &w, &g, jb->row_start + (int)(p / jb->W) * jb->row_stride, (int)(p % jb->W));
+        }
     }
     jb->segments = w.segments;
     jb->tests = w.tests;

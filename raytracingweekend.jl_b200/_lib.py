@@ -43,7 +43,7 @@ EXPORTED_SYMBOLS = (
     "rtw_scene_load",
 )
 
-RTW_ABI_VERSION = 2
+RTW_ABI_VERSION = 3
 
 RTW_OK = 0
 RTW_E_INVALID_ARG = -1
@@ -64,6 +64,9 @@ RTW_OPT_COOP = 7
 RTW_OPT_TAIL = 8
 
 RTW_OPT_WALK = 9
+RTW_OPT_GATHER = 10
+RTW_GATHER_PEER = 0
+RTW_GATHER_NCCL = 1
 RTW_WALK_DEFAULT = 0
 RTW_WALK_SLOTS = 1
 RTW_WALK_OWN_RAY = 2
@@ -135,6 +138,9 @@ class rtw_stats(C.Structure):
         ("ms_resolve", C.c_float),
         ("ms_h2d", C.c_float),
         ("ms_d2h", C.c_float),
+        ("n_devices", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("grid_fallback_rays", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:

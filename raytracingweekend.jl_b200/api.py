@@ -85,6 +85,14 @@ class Renderer:
 
     def set_option(self, option: int, value: int) -> None:
         self._check(self._lib.rtw_set_option(self._ctx, option, int(value)))
+        if option == _lib.RTW_OPT_GATHER:
+            self._gather = int(value)
+
+    def gather_name(self) -> str:
+        """how a multi-device context collects the row tiles (RTW_OPT_GATHER)"""
+        if len(self.devices) == 1:
+            return "none (1 device)"
+        return "NCCL send/recv" if getattr(self, "_gather", 0) == _lib.RTW_GATHER_NCCL else "peer copies"
 
     # -- scene
     def set_scene(self, scene) -> None:

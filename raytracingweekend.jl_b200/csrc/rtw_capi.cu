@@ -1,6 +1,8 @@
 // rtw_capi.cu -- the C-ABI of include/rtw_b200.h: context, buffers, streams, multi-device row split.
 // No C++ exception leaves this file; every entry point returns a status code.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and enums only: the library is bound with dlopen when RTW_GATHER_NCCL is selected
 
 #include <algorithm>
 #include <cmath>
@@ -76,6 +78,11 @@ struct DeviceState {
 struct ProgressiveState {
     bool valid = false;
     int W = 0, s_total = 0, s_done = 0;
+    // what the samples accumulated so far were traced with: a continuation pass must use the same
+    int max_depth = 0;
+    uint64_t seed = 0;
+    uint64_t cam_hash = 0;
+    bool have_inputs = false;  // false after rtw_accumulator_write (a raw checkpoint carries no render inputs)
 };
 
 struct rtw_ctx {
@@ -88,6 +95,10 @@ struct rtw_ctx {
     uint32_t n_spheres64 = 0;
     bool have_scene64 = false;
     rtw::GridParams grid = {};  // host copy of the grid header (device pointers are per device)
+    bool grid_valid = false;    // the grid of the current scene has been built and uploaded (lazily: RTW_MODE_GRID only)
+    std::vector<float> h_geom;  // host copy of geom4, kept for the lazy grid build
+    float max_albedo = 0.f;     // largest albedo component of the scene (fixed-point head-room check)
+    double max_albedo64 = 0.0;  // the same for the Float64 scene
     int mode = RTW_MODE_FUSED;
     int rays_per_lane = 0;  // 0 = default
     int sweep = 0;          // 0 = default
@@ -96,11 +107,25 @@ struct rtw_ctx {
     int walk = 0;           // RTW_WALK_*; 0 = default
     int blocks_per_sm = 0;
     int collect_timing = 1;
+    // framebuffer gather of the multi-device render: peer copies (default) or one grouped NCCL send/recv
+    int gather = RTW_GATHER_PEER;
+    void* nccl_lib = nullptr;
+    std::vector<ncclComm_t> nccl_comm;  // one communicator per device of the context (ncclCommInitAll), created lazily
+    ncclResult_t (*nccl_CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*nccl_CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*nccl_GroupStart)() = nullptr;
+    ncclResult_t (*nccl_GroupEnd)() = nullptr;
+    ncclResult_t (*nccl_Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*nccl_Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*nccl_GetErrorString)(ncclResult_t) = nullptr;
 };
 
 namespace {
 
 // defaults chosen by measurement on B200 (profiles/): see DESIGN.md "Kernel variants"
+// device counters: [0] path tickets, [1] ray segments, [2] rays RTW_MODE_GRID resolved by the exact fallback sweep, [3] spare;
+// the pinned host mirror has 2 * kCounters words (the upper half is scratch of RTW_MODE_WAVEFRONT)
+constexpr int kCounters = 4;
 constexpr int kDefaultRaysPerLane = 1;
 constexpr int kDefaultSweep = RTW_SWEEP_PACKED;
 constexpr int kDefaultCoop = 2;
@@ -122,6 +147,42 @@ int cuda_fail(rtw_ctx* c, cudaError_t e, const char* what) {
     do {                                                      \
         cudaError_t e__ = (call);                             \
         if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+// RTW_GATHER_NCCL: bind libnccl at run time (the process may already hold one, e.g. torch's bundled copy -- the
+// loader then returns that one) and create one communicator per device of the context.
+int ensure_nccl(rtw_ctx* ctx) {
+    if (!ctx->nccl_comm.empty()) return RTW_OK;
+    if (!ctx->nccl_lib) {
+        ctx->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!ctx->nccl_lib) ctx->nccl_lib = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+        if (!ctx->nccl_lib) return fail(ctx, RTW_E_UNSUPPORTED, "RTW_GATHER_NCCL: libnccl.so.2 cannot be loaded");
+        void* h = ctx->nccl_lib;
+        ctx->nccl_CommInitAll = (decltype(ctx->nccl_CommInitAll))dlsym(h, "ncclCommInitAll");
+        ctx->nccl_CommDestroy = (decltype(ctx->nccl_CommDestroy))dlsym(h, "ncclCommDestroy");
+        ctx->nccl_GroupStart = (decltype(ctx->nccl_GroupStart))dlsym(h, "ncclGroupStart");
+        ctx->nccl_GroupEnd = (decltype(ctx->nccl_GroupEnd))dlsym(h, "ncclGroupEnd");
+        ctx->nccl_Send = (decltype(ctx->nccl_Send))dlsym(h, "ncclSend");
+        ctx->nccl_Recv = (decltype(ctx->nccl_Recv))dlsym(h, "ncclRecv");
+        ctx->nccl_GetErrorString = (decltype(ctx->nccl_GetErrorString))dlsym(h, "ncclGetErrorString");
+        if (!ctx->nccl_CommInitAll || !ctx->nccl_CommDestroy || !ctx->nccl_GroupStart || !ctx->nccl_GroupEnd ||
+            !ctx->nccl_Send || !ctx->nccl_Recv || !ctx->nccl_GetErrorString)
+            return fail(ctx, RTW_E_UNSUPPORTED, "RTW_GATHER_NCCL: libnccl lacks a required symbol");
+    }
+    const int G = (int)ctx->dev.size();
+    std::vector<int> devs(G);
+    for (int g = 0; g < G; ++g) devs[g] = ctx->dev[g].device;
+    std::vector<ncclComm_t> comms(G, nullptr);
+    const ncclResult_t r = ctx->nccl_CommInitAll(comms.data(), G, devs.data());
+    if (r != ncclSuccess) return fail(ctx, RTW_E_INTERNAL, std::string("ncclCommInitAll: ") + ctx->nccl_GetErrorString(r));
+    ctx->nccl_comm = comms;
+    return RTW_OK;
+}
+
+#define RTW_NCCL(ctx, call)                                                                                   \
+    do {                                                                                                      \
+        const ncclResult_t r__ = (call);                                                                      \
+        if (r__ != ncclSuccess) return fail(ctx, RTW_E_INTERNAL, std::string(#call ": ") + ctx->nccl_GetErrorString(r__)); \
     } while (0)
 
 template <typename T>
@@ -163,12 +224,23 @@ int fx_bits_for(int spp) {
     return 62 - b - 6;
 }
 
+// The fixed-point accumulator keeps 6 bits (64x) of head-room per path above radiance 1.  A path's radiance is at most
+// max_albedo^(max_depth - 1) (sky <= 1): with every albedo <= 1 -- all of the reference's scenes -- it never exceeds 1.
+// A scene that uses albedo > 1 as emission is accepted as long as that bound stays below 64; beyond it the sums could
+// saturate silently, so the call is refused instead.
+bool radiance_fits_headroom(double max_albedo, int max_depth) {
+    if (!(max_albedo > 1.0) || max_depth <= 1) return true;
+    return (double)(max_depth - 1) * std::log2(max_albedo) <= 6.0;
+}
+
 int check_render_args(rtw_ctx* ctx, const rtw_camera* cam, int W, int spp, int max_depth) {
     if (!cam) return fail(ctx, RTW_E_INVALID_ARG, "camera is NULL");
     if (W < 1 || W > 65536) return fail(ctx, RTW_E_INVALID_ARG, "image_width must be in 1..65536");
     if (spp < 1 || spp > (1 << 24)) return fail(ctx, RTW_E_INVALID_ARG, "n_samples must be in 1..2^24");
     if (max_depth < 0 || max_depth > (1 << 20)) return fail(ctx, RTW_E_INVALID_ARG, "max_depth must be in 0..2^20");
     if (!ctx->have_scene) return fail(ctx, RTW_E_NO_SCENE, "rtw_set_scene has not been called");
+    if (!radiance_fits_headroom(ctx->max_albedo, max_depth))
+        return fail(ctx, RTW_E_UNSUPPORTED, "albedo > 1 with this max_depth can exceed the 64x head-room of the fixed-point accumulator");
     return RTW_OK;
 }
 
@@ -214,6 +286,8 @@ struct PassSpec {
     bool reset;  // zero the accumulator first
 };
 
+int ensure_grid_locked(rtw_ctx* ctx);
+
 // Enqueue the trace of one pass for a row subset on one device (accumulates into ds.d_accum).
 int enqueue_trace(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, int max_depth, uint64_t seed,
                   int row_start, int row_stride, const PassSpec& ps, cudaStream_t stream, bool timing) {
@@ -237,7 +311,7 @@ int enqueue_trace(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, i
     if (rc) return rc;
     if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[0], stream));
     if (ps.reset) RTW_CUDA(ctx, cudaMemsetAsync(ds.d_accum, 0, npix * 4 * sizeof(unsigned long long), stream));
-    RTW_CUDA(ctx, cudaMemsetAsync(ds.d_counters, 0, 2 * sizeof(unsigned long long), stream));
+    RTW_CUDA(ctx, cudaMemsetAsync(ds.d_counters, 0, kCounters * sizeof(unsigned long long), stream));
 
     const int fx_bits = fx_bits_for(ps.s_total);
     int launches = 0;
@@ -262,11 +336,15 @@ int enqueue_trace(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, i
         p.fx_scale = std::ldexp(1.0, fx_bits);
         p.counters = ds.d_counters;
         rtw::LaunchInfo li{};
-        p.grid = ctx->grid;
-        p.grid.cell_start = ds.d_grid_start;
-        p.grid.items = ds.d_grid_items;
-        p.grid.big = ds.d_grid_big;
+        p.grid = rtw::GridParams{};
         if (ctx->mode == RTW_MODE_GRID) {
+            rc = ensure_grid_locked(ctx);  // no-op unless this is the first grid-mode trace of the scene
+            if (rc) return rc;
+            RTW_CUDA(ctx, cudaSetDevice(ds.device));
+            p.grid = ctx->grid;
+            p.grid.cell_start = ds.d_grid_start;
+            p.grid.items = ds.d_grid_items;
+            p.grid.big = ds.d_grid_big;
             rc = grow(ctx, &ds.d_uv, &ds.uv_cap, (size_t)W + (size_t)H);
             if (rc) return rc;
             RTW_CUDA(ctx, rtw::launch_uv_tables(W, H, ds.d_uv, ds.d_uv + W, stream));
@@ -288,7 +366,7 @@ int enqueue_trace(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, i
             rtw::WavefrontBuffers b;
             rc = wavefront_buffers(ctx, ds, p.n_paths, &b);
             if (rc) return rc;
-            RTW_CUDA(ctx, rtw::launch_wavefront_trace(p, b, ds.num_sms, (unsigned int*)(ds.h_counters + 2), stream, &li));
+            RTW_CUDA(ctx, rtw::launch_wavefront_trace(p, b, ds.num_sms, (unsigned int*)(ds.h_counters + kCounters), stream, &li));
         } else {
             const int rays = ctx->rays_per_lane > 0 ? ctx->rays_per_lane : kDefaultRaysPerLane;
             const int sweep = ctx->sweep > 0 ? ctx->sweep : kDefaultSweep;
@@ -317,8 +395,8 @@ int enqueue_trace(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, i
         launches += li.launches;
     }
     if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[1], stream));
-    RTW_CUDA(ctx, cudaMemcpyAsync(ds.h_counters, ds.d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                                  stream));
+    RTW_CUDA(ctx, cudaMemcpyAsync(ds.h_counters, ds.d_counters, kCounters * sizeof(unsigned long long),
+                                  cudaMemcpyDeviceToHost, stream));
     ds.last.kernel_launches = launches;
     ds.last_resolved = false;
     return RTW_OK;
@@ -352,6 +430,7 @@ int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, in
 // after the stream has been synchronised: fill counters / timings
 int finish_stats(rtw_ctx* ctx, DeviceState& ds, bool timing) {
     ds.last.ray_segments = ds.h_counters[1];
+    ds.last.grid_fallback_rays = ds.h_counters[2];
     ds.last.sphere_tests = ds.last.ray_segments * (uint64_t)ctx->n_spheres;
     if (timing && ds.last.rows_rendered > 0) {
         float a = 0.f, b = 0.f;
@@ -401,13 +480,24 @@ void build_grid(const float* geom4, uint32_t n, HostGrid* out) {
     auto dims = [&](double hh, int* nd) {
         double cells = 1.0;
         for (int a = 0; a < 3; ++a) {
-            nd[a] = (int)std::floor((hi[a] - lo[a]) / hh) + 2;  // one cell of slack around the inflated boxes
-            cells *= nd[a];
+            // one cell of slack around the inflated boxes; formed in double and clamped before the conversion (an
+            // extreme extent / radius ratio must not overflow the int)
+            const double want = std::floor((hi[a] - lo[a]) / hh) + 2.0;
+            nd[a] = want < 1.0e6 ? (int)want : 1000000;
+            cells *= want;
         }
         return cells;
     };
     int nd[3];
-    while (dims(h, nd) > 2.0 * (double)small.size() + 64.0 || nd[0] > 1024 || nd[1] > 1024 || nd[2] > 1024) h *= 1.25;
+    int grow_steps = 0;
+    while (dims(h, nd) > 2.0 * (double)small.size() + 64.0 || nd[0] > 1024 || nd[1] > 1024 || nd[2] > 1024) {
+        h *= 1.25;
+        if (++grow_steps > 4096 || !std::isfinite(h)) {  // degenerate extent: no grid, every sphere is tested by every ray
+            g.big.clear();
+            for (uint32_t i = 0; i < n; ++i) g.big.push_back(i);
+            return;
+        }
+    }
     const double inflate = 0.05 * h;  // registration margin: rounding of the traversal AND the reference's a = 1 shortcut
     double r_min = 1e300;
     for (uint32_t i : small) r_min = std::min(r_min, (double)radii[i]);
@@ -454,11 +544,58 @@ void build_grid(const float* geom4, uint32_t n, HostGrid* out) {
     }
 }
 
+// RTW_MODE_GRID only, on first use after rtw_set_scene: build the grid from the host copy of the geometry and upload
+// it to every device of the context (the default mode never pays for it)
+int ensure_grid_locked(rtw_ctx* ctx) {
+    if (ctx->grid_valid) return RTW_OK;
+    HostGrid hg;
+    build_grid(ctx->h_geom.data(), ctx->n_spheres, &hg);
+    for (auto& ds : ctx->dev) {
+        RTW_CUDA(ctx, cudaSetDevice(ds.device));
+        int grc = grow(ctx, &ds.d_grid_start, &ds.grid_start_cap, hg.cell_start.size());
+        if (!grc) grc = grow(ctx, &ds.d_grid_items, &ds.grid_items_cap, hg.items.size());
+        if (!grc) grc = grow(ctx, &ds.d_grid_big, &ds.grid_big_cap, hg.big.size());
+        if (grc) return grc;
+        if (!hg.cell_start.empty())
+            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_grid_start, hg.cell_start.data(), hg.cell_start.size() * 4, cudaMemcpyHostToDevice, ds.stream));
+        if (!hg.items.empty())
+            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_grid_items, hg.items.data(), hg.items.size() * 4, cudaMemcpyHostToDevice, ds.stream));
+        if (!hg.big.empty())
+            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_grid_big, hg.big.data(), hg.big.size() * 4, cudaMemcpyHostToDevice, ds.stream));
+    }
+    for (auto& ds : ctx->dev) {  // the host vectors die with this call
+        RTW_CUDA(ctx, cudaSetDevice(ds.device));
+        RTW_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+    }
+    ctx->grid = hg.hdr;
+    ctx->grid.n_big = (uint32_t)hg.big.size();
+    ctx->grid_valid = true;
+    return RTW_OK;
+}
+
 int set_scene_locked(rtw_ctx* ctx, const float* geom4, const float* mat4, const uint32_t* kind, uint32_t n) {
     if (n > 0 && (!geom4 || !mat4 || !kind)) return fail(ctx, RTW_E_INVALID_ARG, "scene arrays are NULL");
     if (n > (1u << 26)) return fail(ctx, RTW_E_INVALID_ARG, "too many spheres");
-    for (uint32_t i = 0; i < n; ++i)
+    float max_albedo = 0.f;
+    for (uint32_t i = 0; i < n; ++i) {
         if (kind[i] > RTW_DIELECTRIC) return fail(ctx, RTW_E_UNSUPPORTED, "unknown material kind (only Lambertian/Metal/Dielectric)");
+        if (kind[i] != RTW_DIELECTRIC)
+            for (int c = 0; c < 3; ++c) {
+                const float a = mat4[4 * (size_t)i + c];
+                if (!std::isfinite(a) || a < 0.f)
+                    return fail(ctx, RTW_E_UNSUPPORTED, "albedo components must be finite and >= 0 (fixed-point accumulator)");
+                max_albedo = std::max(max_albedo, a);
+            }
+    }
+    // From here on the previous scene is gone: a failure below must not leave a context that claims to hold one
+    // (device arrays freed / half uploaded).  Re-validated only after every device has synchronised.
+    ctx->have_scene = false;
+    ctx->n_spheres = 0;
+    ctx->grid_valid = false;
+    ctx->grid = rtw::GridParams{};
+    ctx->prog = ProgressiveState{};  // a progressive image belongs to the scene it was traced on
+    ctx->h_geom.assign(geom4, geom4 + 4 * (size_t)n);  // for the lazy grid build (RTW_MODE_GRID only)
+    ctx->max_albedo = max_albedo;
     // pair layout of the geometry for the packed sweep: spheres (2p, 2p+1) -> {xa,xb,ya,yb}{za,zb,ra,rb}
     std::vector<float> pairs((size_t)((n + 1u) / 2u) * 8u, 0.0f);
     for (uint32_t i = 0; i < n; ++i) {
@@ -484,23 +621,6 @@ int set_scene_locked(rtw_ctx* ctx, const float* geom4, const float* mat4, const 
                 std::memcpy(perm[v].data() + ((size_t)(c * coop + h) * 32u + j) * 4u, geom4 + 4 * (size_t)kl, 16);
             }
         }
-    }
-    HostGrid hg;
-    build_grid(geom4, n, &hg);
-    ctx->grid = hg.hdr;
-    ctx->grid.n_big = (uint32_t)hg.big.size();
-    for (auto& ds : ctx->dev) {
-        RTW_CUDA(ctx, cudaSetDevice(ds.device));
-        int grc = grow(ctx, &ds.d_grid_start, &ds.grid_start_cap, hg.cell_start.size());
-        if (!grc) grc = grow(ctx, &ds.d_grid_items, &ds.grid_items_cap, hg.items.size());
-        if (!grc) grc = grow(ctx, &ds.d_grid_big, &ds.grid_big_cap, hg.big.size());
-        if (grc) return grc;
-        if (!hg.cell_start.empty())
-            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_grid_start, hg.cell_start.data(), hg.cell_start.size() * 4, cudaMemcpyHostToDevice, ds.stream));
-        if (!hg.items.empty())
-            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_grid_items, hg.items.data(), hg.items.size() * 4, cudaMemcpyHostToDevice, ds.stream));
-        if (!hg.big.empty())
-            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_grid_big, hg.big.data(), hg.big.size() * 4, cudaMemcpyHostToDevice, ds.stream));
     }
     for (auto& ds : ctx->dev) {
         RTW_CUDA(ctx, cudaSetDevice(ds.device));
@@ -570,6 +690,7 @@ int pass_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int max_depth, uint6
             ds.last.image_height = H;
             ds.last_resolved = false;
             ds.h_counters[1] = 0;
+            ds.h_counters[2] = 0;
         }
     }
     if (do_resolve) {
@@ -584,6 +705,11 @@ int pass_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int max_depth, uint6
             const size_t tile_floats = (size_t)rows_pad * W * 3;
             rc = grow(ctx, &d0.d_gather, &d0.gather_cap, tile_floats * G);
             if (rc) return rc;
+            const bool use_nccl = ctx->gather == RTW_GATHER_NCCL;
+            if (use_nccl) {
+                rc = ensure_nccl(ctx);
+                if (rc) return rc;
+            }
             for (int g = 0; g < G; ++g) {
                 DeviceState& ds = ctx->dev[g];
                 RTW_CUDA(ctx, cudaSetDevice(ds.device));
@@ -596,7 +722,7 @@ int pass_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int max_depth, uint6
                 }
                 rc = enqueue_resolve(ctx, ds, W, g, G, 0, divisor, ps.s_total, tile, ds.stream, timing);
                 if (rc) return rc;
-                if (g != 0) {
+                if (g != 0 && !use_nccl) {
                     // framebuffer gather: tile -> device 0 over NVLink (peer copy on the producer's stream)
                     size_t bytes = (size_t)rows_of(H, g, G) * W * 3 * sizeof(float);
                     if (bytes) RTW_CUDA(ctx, cudaMemcpyPeerAsync(dst, d0.device, tile, ds.device, bytes, ds.stream));
@@ -604,7 +730,21 @@ int pass_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int max_depth, uint6
                 }
             }
             RTW_CUDA(ctx, cudaSetDevice(d0.device));
-            for (int g = 1; g < G; ++g) RTW_CUDA(ctx, cudaStreamWaitEvent(d0.stream, ctx->dev[g].ev_tile, 0));
+            if (use_nccl) {
+                // the single NCCL gather: every device sends its tile to device 0, which receives them behind its own
+                // resolve -- one grouped call, the streams of the context carry the ordering
+                RTW_NCCL(ctx, ctx->nccl_GroupStart());
+                for (int g = 1; g < G; ++g) {
+                    const size_t count = (size_t)rows_of(H, g, G) * W * 3;
+                    if (!count) continue;
+                    RTW_NCCL(ctx, ctx->nccl_Send(ctx->dev[g].d_tile, count, ncclFloat, 0, ctx->nccl_comm[g], ctx->dev[g].stream));
+                    RTW_NCCL(ctx, ctx->nccl_Recv(d0.d_gather + tile_floats * g, count, ncclFloat, g, ctx->nccl_comm[0], d0.stream));
+                }
+                RTW_NCCL(ctx, ctx->nccl_GroupEnd());
+                RTW_CUDA(ctx, cudaSetDevice(d0.device));
+            } else {
+                for (int g = 1; g < G; ++g) RTW_CUDA(ctx, cudaStreamWaitEvent(d0.stream, ctx->dev[g].ev_tile, 0));
+            }
             RTW_CUDA(ctx, rtw::launch_assemble(d0.d_gather, G, W, H, d0.d_image, d0.stream));
         }
     }
@@ -641,6 +781,7 @@ int pass_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int max_depth, uint6
         }
         total.paths += ds.last.paths;
         total.ray_segments += ds.last.ray_segments;
+        total.grid_fallback_rays += ds.last.grid_fallback_rays;
         total.sphere_tests += ds.last.sphere_tests;
         total.rows_rendered += ds.last.rows_rendered;
         total.kernel_launches += ds.last.kernel_launches;
@@ -648,6 +789,7 @@ int pass_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int max_depth, uint6
         total.ms_resolve = std::fmax(total.ms_resolve, ds.last.ms_resolve);
     }
     total.kernel_launches += extra_launches;
+    total.n_devices = G;
     RTW_CUDA(ctx, cudaSetDevice(d0.device));
     float ms = 0.f;
     RTW_CUDA(ctx, cudaEventElapsedTime(&ms, d0.ev[3], d0.ev[5]));
@@ -676,6 +818,18 @@ int set_scene_f64_locked(rtw_ctx* ctx, const double* geom4, const double* mat4, 
     if (n > (1u << 26)) return fail(ctx, RTW_E_INVALID_ARG, "too many spheres");
     for (uint32_t i = 0; i < n; ++i)
         if (kind[i] > RTW_DIELECTRIC) return fail(ctx, RTW_E_UNSUPPORTED, "unknown material kind (only Lambertian/Metal/Dielectric)");
+    double max_albedo = 0.0;
+    for (uint32_t i = 0; i < n; ++i)
+        if (kind[i] != RTW_DIELECTRIC)
+            for (int c = 0; c < 3; ++c) {
+                const double a = mat4[4 * (size_t)i + c];
+                if (!std::isfinite(a) || a < 0.0)
+                    return fail(ctx, RTW_E_UNSUPPORTED, "albedo components must be finite and >= 0 (fixed-point accumulator)");
+                max_albedo = std::max(max_albedo, a);
+            }
+    ctx->have_scene64 = false;  // failure-atomic: see set_scene_locked
+    ctx->n_spheres64 = 0;
+    ctx->max_albedo64 = max_albedo;
     for (auto& ds : ctx->dev) {
         RTW_CUDA(ctx, cudaSetDevice(ds.device));
         if (n > ds.scene64_cap || !ds.d_geom64) {
@@ -709,6 +863,8 @@ int render_f64_locked(rtw_ctx* ctx, const rtw_camera_f64* cam, int W, int spp, i
     if (spp < 1 || spp > (1 << 24)) return fail(ctx, RTW_E_INVALID_ARG, "n_samples must be in 1..2^24");
     if (max_depth < 0 || max_depth > (1 << 20)) return fail(ctx, RTW_E_INVALID_ARG, "max_depth must be in 0..2^20");
     if (!ctx->have_scene64) return fail(ctx, RTW_E_NO_SCENE, "rtw_set_scene_f64 has not been called");
+    if (!radiance_fits_headroom(ctx->max_albedo64, max_depth))
+        return fail(ctx, RTW_E_UNSUPPORTED, "albedo > 1 with this max_depth can exceed the 64x head-room of the fixed-point accumulator");
     if (!out_rgb) return fail(ctx, RTW_E_INVALID_ARG, "out_rgb is NULL");
     ctx->prog = ProgressiveState{};  // the accumulators are reused
     const int H = rtw_image_height(W);
@@ -749,7 +905,7 @@ int render_f64_locked(rtw_ctx* ctx, const rtw_camera_f64* cam, int W, int spp, i
         if (rc) return rc;
         if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[0], ds.stream));
         RTW_CUDA(ctx, cudaMemsetAsync(ds.d_accum, 0, npix * 4 * sizeof(unsigned long long), ds.stream));
-        RTW_CUDA(ctx, cudaMemsetAsync(ds.d_counters, 0, 2 * sizeof(unsigned long long), ds.stream));
+        RTW_CUDA(ctx, cudaMemsetAsync(ds.d_counters, 0, kCounters * sizeof(unsigned long long), ds.stream));
         int launches = 0;
         if (max_depth > 0) {
             rtw::TraceParams64 p;
@@ -778,8 +934,8 @@ int render_f64_locked(rtw_ctx* ctx, const rtw_camera_f64* cam, int W, int spp, i
             launches += li.launches;
         }
         if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[1], ds.stream));
-        RTW_CUDA(ctx, cudaMemcpyAsync(ds.h_counters, ds.d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                                      ds.stream));
+        RTW_CUDA(ctx, cudaMemcpyAsync(ds.h_counters, ds.d_counters, kCounters * sizeof(unsigned long long),
+                                      cudaMemcpyDeviceToHost, ds.stream));
         double* dst = G == 1 ? d0.d_image64 : d0.d_gather64 + tile_vals * g;
         double* tile = dst;
         if (g != 0) {
@@ -837,6 +993,7 @@ int render_f64_locked(rtw_ctx* ctx, const rtw_camera_f64* cam, int W, int spp, i
         total.ms_resolve = std::fmax(total.ms_resolve, ds.last.ms_resolve);
     }
     if (G > 1) total.kernel_launches += 1;
+    total.n_devices = G;
     RTW_CUDA(ctx, cudaSetDevice(d0.device));
     float ms = 0.f;
     RTW_CUDA(ctx, cudaEventElapsedTime(&ms, d0.ev[3], d0.ev[5]));
@@ -903,15 +1060,15 @@ int rtw_create(const int* device_ids, int n_devices, rtw_ctx** out_ctx) {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ds.stream, cudaStreamNonBlocking);
         for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&ds.ev[i]);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ds.ev_tile, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&ds.d_counters, 2 * sizeof(unsigned long long));
-        if (e == cudaSuccess) e = cudaMallocHost((void**)&ds.h_counters, 4 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&ds.d_counters, kCounters * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&ds.h_counters, 2 * kCounters * sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaMalloc((void**)&ds.d_scratch, 4u << 20);
         if (e != cudaSuccess) {
             (void)cudaGetLastError();
             rtw_destroy(ctx);
             return (int)e;
         }
-        ds.h_counters[0] = ds.h_counters[1] = 0;
+        for (int i = 0; i < 2 * kCounters; ++i) ds.h_counters[i] = 0;
     }
     // enable peer access towards device 0 for the tile gather (ignored when unavailable: the copy is then staged)
     for (int g = 1; g < n_devices; ++g) {
@@ -928,6 +1085,14 @@ int rtw_create(const int* device_ids, int n_devices, rtw_ctx** out_ctx) {
 
 int rtw_destroy(rtw_ctx* ctx) {
     if (!ctx) return RTW_OK;
+    for (size_t g = 0; g < ctx->nccl_comm.size(); ++g) {
+        if (!ctx->nccl_comm[g] || g >= ctx->dev.size()) continue;
+        if (cudaSetDevice(ctx->dev[g].device) == cudaSuccess) {
+            cudaStreamSynchronize(ctx->dev[g].stream);
+            ctx->nccl_CommDestroy(ctx->nccl_comm[g]);
+        }
+    }
+    ctx->nccl_comm.clear();
     for (auto& ds : ctx->dev) {
         if (cudaSetDevice(ds.device) != cudaSuccess) continue;
         if (ds.stream) cudaStreamSynchronize(ds.stream);
@@ -991,6 +1156,10 @@ int rtw_set_option(rtw_ctx* ctx, int option, int64_t value) {
             return RTW_OK;
         case RTW_OPT_COLLECT_TIMING:
             ctx->collect_timing = value != 0;
+            return RTW_OK;
+        case RTW_OPT_GATHER:
+            if (value != RTW_GATHER_PEER && value != RTW_GATHER_NCCL) return fail(ctx, RTW_E_INVALID_ARG, "unknown gather");
+            ctx->gather = (int)value;
             return RTW_OK;
         default:
             return fail(ctx, RTW_E_UNSUPPORTED, "unknown option");
@@ -1133,11 +1302,17 @@ int rtw_accumulate(rtw_ctx* ctx, const rtw_camera* cam, int image_width, int sam
         if (sample_first < 0 || sample_count < 1 || sample_first > n_samples_total - sample_count)
             return fail(ctx, RTW_E_INVALID_ARG, "samples must satisfy 0 <= first, 1 <= count, first + count <= total");
         ProgressiveState& pg = ctx->prog;
+        uint64_t cam_hash = 1469598103934665603ull;  // FNV-1a over the 88 bytes of the camera
+        for (size_t i = 0; i < sizeof(rtw_camera); ++i) cam_hash = (cam_hash ^ ((const unsigned char*)cam)[i]) * 1099511628211ull;
         if (sample_first != 0) {
             if (!pg.valid || pg.W != image_width || pg.s_total != n_samples_total || pg.s_done != sample_first)
                 return fail(ctx, RTW_E_INVALID_ARG, "sample_first must continue the progressive image held by the context "
                                                     "(same width and total, first == samples accumulated so far)");
+            if (pg.have_inputs && (pg.seed != seed || pg.max_depth != max_depth || pg.cam_hash != cam_hash))
+                return fail(ctx, RTW_E_INVALID_ARG, "a continuation pass must use the seed, max_depth and camera the "
+                                                    "progressive image was started with");
         }
+        const bool had_inputs = sample_first != 0 ? pg.have_inputs : true;
         const PassSpec ps{sample_first, sample_count, n_samples_total, sample_first == 0};
         pg.valid = false;  // stays invalid if the pass fails half-way
         rc = pass_locked(ctx, cam, image_width, max_depth, seed, ps, true, false, 0, nullptr, nullptr, stats, false);
@@ -1146,6 +1321,13 @@ int rtw_accumulate(rtw_ctx* ctx, const rtw_camera* cam, int image_width, int sam
         pg.W = image_width;
         pg.s_total = n_samples_total;
         pg.s_done = sample_first + sample_count;
+        pg.have_inputs = had_inputs;
+        if (sample_first == 0 || !had_inputs) {
+            pg.seed = seed;
+            pg.max_depth = max_depth;
+            pg.cam_hash = cam_hash;
+            pg.have_inputs = true;  // from here on the inputs are pinned (also after a raw-checkpoint resume)
+        }
         return RTW_OK;
     } catch (...) {
         return fail(ctx, RTW_E_INTERNAL, "unexpected C++ exception in rtw_accumulate");

@@ -411,6 +411,7 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
     float best_t = __int_as_float(0x7f800000);
     int best_k = -1;
     uint32_t seg_count = 0;
+    uint32_t fb_count = 0;  // kGrid: rays of this warp resolved by the exact fallback sweep (uniform)
     unsigned long long pool_next = 0, pool_end = 0;  // warp-level ticket pool (uniform)
     bool exhausted = false;
 
@@ -633,10 +634,10 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
         best_t = __int_as_float(0x7f800000);  // typemax(T) = Inf, src/ray_color.jl:19
         best_k = -1;
         if (kGrid) {
-            const bool unsafe = closest_hit_grid(P.grid, P.geom, o, d, alive, n <= kGridFallbackMax, best_t, best_k);
+            const bool unsafe = closest_hit_grid(P.grid, P.geom, o, d, alive, best_t, best_k);
             // rays the grid cannot answer exactly (non-unit direction after a glass reflection, very long flights):
-            // warp-cooperative sweep of the whole list; for lists > kGridFallbackMax the grid answer stands
-            if (n <= kGridFallbackMax) grid_fallback_sweep(P.geom, n, o, d, unsafe, best_t, best_k);
+            // warp-cooperative sweep of the whole list, for every list size -- the mode is exact by construction
+            fb_count += grid_fallback_sweep(P.geom, n, o, d, unsafe, best_t, best_k);
         } else {
             const uint32_t h = threadIdx.x & (kCoop - 1);
             f3 so[kCoop], sd[kCoop];
@@ -689,6 +690,7 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
     // ray-segment statistics: one atomic per warp
     for (int off = 16; off > 0; off >>= 1) seg_count += __shfl_xor_sync(kFullMask, seg_count, off);
     if (lane == 0 && seg_count) atomicAdd(P.counters + 1, (unsigned long long)seg_count);
+    if (kGrid && lane == 0 && fb_count) atomicAdd(P.counters + 2, (unsigned long long)fb_count);
 }
 
 // u_tab[col] = T((col+1)/W), v_tab[i0] = T((H-1-i0)/H) (src/render.jl:26-27): the quotient is formed in Float64 and

@@ -48,13 +48,10 @@ __device__ __forceinline__ void grid_test_sphere(const float4 s, uint32_t k, con
     }
 }
 
-constexpr uint32_t kGridFallbackMax = 4096;  // lists up to this size resolve unsafe rays exactly (cooperative sweep)
-
-// returns true when the ray is "unsafe" for the grid (see above) and can_fallback is set: the result is then NOT
-// final and the caller must run grid_fallback_sweep; without can_fallback the grid answer is returned regardless
+// returns true when the ray is "unsafe" for the grid (see above): the result is then NOT final and the caller must
+// run grid_fallback_sweep
 __device__ __forceinline__ bool closest_hit_grid(const GridParams& G, const float4* __restrict__ geom, const f3 o,
-                                                 const f3 d, const bool alive, const bool can_fallback, float& best_t,
-                                                 int& best_k) {
+                                                 const f3 d, const bool alive, float& best_t, int& best_k) {
     float bt = __int_as_float(0x7f800000);  // typemax(T) = Inf, src/ray_color.jl:19
     int bk = -1;
     bool unsafe = false;
@@ -125,7 +122,7 @@ __device__ __forceinline__ bool closest_hit_grid(const GridParams& G, const floa
                 t_far = eps > 1e-6f ? sqrtf(mx * mx + my * my + mz * mz) + 0.5f * sqrtf(hx * hx + hy * hy + hz * hz) : 0.0f;
             }
             t_far = fminf(t_far, bt + 2.0f * G.h);
-            unsafe = can_fallback && eps * t_far * t_far > G.safe2;
+            unsafe = eps * t_far * t_far > G.safe2;
         }
     }
     best_t = bt;
@@ -135,10 +132,12 @@ __device__ __forceinline__ bool closest_hit_grid(const GridParams& G, const floa
 
 // Exact closest hit for the unsafe rays of a warp: one ray at a time, the 32 lanes split the list, the partial
 // results are reduced with the tie rule (equal t: larger index).  Called by all lanes of the warp.
-__device__ __forceinline__ void grid_fallback_sweep(const float4* __restrict__ geom, uint32_t n, const f3 o, const f3 d,
-                                                    bool unsafe, float& best_t, int& best_k) {
+// Returns the number of rays of the warp it resolved (uniform).
+__device__ __forceinline__ uint32_t grid_fallback_sweep(const float4* __restrict__ geom, uint32_t n, const f3 o, const f3 d,
+                                                        bool unsafe, float& best_t, int& best_k) {
     const unsigned lane = threadIdx.x & 31u;
     unsigned pending = __ballot_sync(0xffffffffu, unsafe);
+    const uint32_t resolved = (uint32_t)__popc(pending);
     while (pending) {
         const int src = __ffs((int)pending) - 1;
         pending &= pending - 1u;
@@ -161,6 +160,7 @@ __device__ __forceinline__ void grid_fallback_sweep(const float4* __restrict__ g
             best_k = bk;
         }
     }
+    return resolved;
 }
 
 }  // namespace

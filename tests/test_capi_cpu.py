@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(rtw):
 
 def test_abi_version_and_image_height(rtw):
     lib = rtw._lib.load()
-    assert lib.rtw_abi_version() == 2
+    assert lib.rtw_abi_version() == 3
     for w, h in [(96, 54), (400, 225), (1920, 1080), (200, 112), (1, 0)]:
         assert lib.rtw_image_height(w) == h
 
@@ -50,7 +50,7 @@ def test_struct_layouts_match_header_and_julia(rtw):
     body = text[text.index("typedef struct rtw_stats {"):text.index("} rtw_stats;")]
     fields = re.findall(r"\b([a-z_0-9]+);", body)
     assert fields == [n for n, _ in rtw.rtw_stats._fields_]
-    assert C.sizeof(rtw.rtw_stats) == 64
+    assert C.sizeof(rtw.rtw_stats) == 80
     cam = rtw.t_cam1()
     assert cam.as_array().shape == (22,) and cam.as_array().dtype == np.float32
 

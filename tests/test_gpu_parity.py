@@ -718,3 +718,62 @@ def test_progressive_and_float64_on_several_devices(rtw, scenes):
         assert np.array_equal(a, b)
         r2.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_GRID)
         assert np.array_equal(np.array(r2.render(cam, W, total, max_depth=16, seed=5, scene=scenes["random"])), full)
+
+
+# ---- parity ON the headline configurations themselves (BASELINE configs[2..4]) ------------------------------------
+@pytest.mark.parametrize("row", [0, 400, 700, 1079])
+def test_cfg3_headline_rows_match_the_oracle(rtw, oracle, renderer, scenes, row):
+    # BASELINE configs[2]: 1920x1080, 1000 spp, depth 50, seed 1 -- single image rows at FULL width and FULL sample
+    # count against the oracle (src/render.jl:23-40): the W = 1920 u/v tables, the multiply-shift division by 1920 and
+    # 1000, and the 1000-spp fixed-point scale are exactly the ones the benchmark uses.  7.9 M ray segments per row.
+    torch = pytest.importorskip("torch")
+    W, H, spp, depth = 1920, 1080, 1000, 50
+    cam = rtw.t_cam1()
+    renderer.set_scene(scenes["random"])
+    tile = torch.zeros((1, W, 3), dtype=torch.float32, device="cuda:0")
+    stream = torch.cuda.current_stream().cuda_stream
+    renderer.render_rows_device(cam, W, spp, tile.data_ptr(), max_depth=depth, seed=1, row_start=row, row_stride=H,
+                                stream=stream)
+    st = renderer.stats()
+    torch.cuda.synchronize()
+    ref, _, ost = oracle.render(*scenes["random"], cam.as_array(), W, spp, max_depth=depth, seed=1, row_start=row,
+                                row_stride=H)
+    assert st["paths"] == ost["paths"] == W * spp
+    assert st["ray_segments"] == ost["ray_segments"]  # every one of the 1.92 M paths takes the same branches
+    _compare(tile.cpu().numpy()[0], np.ascontiguousarray(ref[row]))
+
+
+def test_cfg3_full_frame_matches_the_oracle(rtw, oracle, renderer, scenes):
+    # the whole 1920x1080 frame, depth 50, at 2 spp (sample 0 centred, sample 1 jittered): every pixel of the
+    # benchmark image geometry is compared with the oracle, 4.1 M paths
+    cam = rtw.t_cam1()
+    img = renderer.render(cam, 1920, 2, max_depth=50, seed=1, scene=scenes["random"])
+    st = dict(renderer.last_stats)
+    ref, _, ost = oracle.render(*scenes["random"], cam.as_array(), 1920, 2, max_depth=50, seed=1)
+    assert st["ray_segments"] == ost["ray_segments"]
+    _compare(img, ref)
+
+
+@pytest.mark.parametrize("mode", ["linear", "grid"])
+def test_cfg5_headline_width_row_matches_the_oracle(rtw, oracle, renderer, mode):
+    # BASELINE configs[4]: the ~100k-sphere list at the benchmark width 1920 and depth 50, one ground row, 2 spp, in
+    # the TMA-streamed linear sweep and in RTW_MODE_GRID
+    torch = pytest.importorskip("torch")
+    rtw.reseed()
+    scene = rtw.flatten_scene(rtw.scene_random_spheres(half_extent=158))
+    W, H, spp, depth, row = 1920, 1080, 2, 50, 640
+    cam = rtw.t_cam1()
+    if mode == "grid":
+        renderer.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_GRID)
+    try:
+        renderer.set_scene(scene)
+        tile = torch.zeros((1, W, 3), dtype=torch.float32, device="cuda:0")
+        renderer.render_rows_device(cam, W, spp, tile.data_ptr(), max_depth=depth, seed=1, row_start=row, row_stride=H,
+                                    stream=torch.cuda.current_stream().cuda_stream)
+        st = renderer.stats()
+        torch.cuda.synchronize()
+    finally:
+        renderer.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_FUSED)
+    ref, _, ost = oracle.render(*scene, cam.as_array(), W, spp, max_depth=depth, seed=1, row_start=row, row_stride=H)
+    assert st["ray_segments"] == ost["ray_segments"]
+    _compare(tile.cpu().numpy()[0], np.ascontiguousarray(ref[row]))

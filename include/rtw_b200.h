@@ -93,7 +93,7 @@ typedef struct rtw_ctx rtw_ctx;
 
 /* ---- options for rtw_set_option -------------------------------------------------------------- */
 #define RTW_OPT_MODE 1            /* RTW_MODE_*                                                        */
-#define RTW_OPT_STRIP 2           /* reserved (accepted, ignored)                                      */
+#define RTW_OPT_STRIP 2           /* removed in ABI v3: RTW_E_UNSUPPORTED                              */
 #define RTW_OPT_BLOCKS_PER_SM 3   /* persistent CTAs per SM (0 = library default)                      */
 #define RTW_OPT_COLLECT_TIMING 4  /* 1 = record per-stage CUDA-event timings into rtw_stats (default 1) */
 #define RTW_OPT_RAYS_PER_LANE 5   /* paths traced concurrently by one lane: 1, 2 or 4 (0 = library default) */
@@ -136,6 +136,11 @@ typedef struct rtw_ctx rtw_ctx;
 /* ---- life cycle ------------------------------------------------------------------------------ */
 
 RTW_API int rtw_abi_version(void);
+
+/* 1 when the library was built with RTW_BUILD_VARIANTS=1 (csrc/build.sh): the kernel families kept only as measured
+ * comparisons -- RTW_TAIL_SPLIT, RTW_SWEEP_BRANCH/MASK, rays per lane 2/4, RTW_OPT_COOP 1/4, RTW_WALK_SLOTS,
+ * RTW_MODE_CTA_WAVEFRONT -- are then selectable; the default build returns RTW_E_UNSUPPORTED for them. */
+RTW_API int rtw_has_variants(void);
 
 /* number of visible CUDA devices (0 and RTW_E_NO_DEVICE when there is none) */
 RTW_API int rtw_device_count(int* count);

@@ -14,7 +14,7 @@ from ._lib import (EXPORTED_SYMBOLS, LIB_PATH, RTW_MODE_CTA_WAVEFRONT, RTW_MODE_
                    RTW_OPT_COLLECT_TIMING, RTW_OPT_COOP, RTW_OPT_MODE, RTW_OPT_RAYS_PER_LANE, RTW_OPT_STRIP, RTW_OPT_SWEEP,
                    RTW_OPT_TAIL, RTW_OPT_WALK, RTW_WALK_DEFAULT, RTW_WALK_OWN_RAY, RTW_WALK_SLOTS, RTW_TAIL_DEFAULT, RTW_TAIL_SPLIT, RTW_TAIL_UNIFIED, RtwError, rtw_camera, rtw_stats)
 from . import sharding
-from .api import (DEFAULT_MAX_DEPTH, DEFAULT_SEED, Renderer, render, scene_load, scene_save, write_png, write_ppm)
+from .api import (DEFAULT_MAX_DEPTH, DEFAULT_SEED, Renderer, has_variants, render, scene_load, scene_save, write_png, write_ppm)
 from .host import (TRNG, Camera, Dielectric, HittableList, Lambertian, Metal, Sphere, Vec3, Xoroshiro128Plus,
                    default_camera, flatten_scene, image_height, near_zero, random_between, reseed,
                    scene_2_spheres, scene_4_spheres, scene_blue_red_spheres, scene_diel_spheres,

@@ -10,11 +10,13 @@ import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "csrc" / "librtw_b200.so"
+# RTW_B200_LIB selects another build of the same library, e.g. csrc/librtw_b200_variants.so (RTW_BUILD_VARIANTS=1)
+LIB_PATH = Path(os.environ["RTW_B200_LIB"]) if os.environ.get("RTW_B200_LIB") else _HERE / "csrc" / "librtw_b200.so"
 
 # every symbol include/rtw_b200.h declares (tests check the .so exports all of them)
 EXPORTED_SYMBOLS = (
     "rtw_abi_version",
+    "rtw_has_variants",
     "rtw_device_count",
     "rtw_image_height",
     "rtw_create",
@@ -167,6 +169,8 @@ def load() -> C.CDLL:
     u32p = C.POINTER(C.c_uint32)
     lib.rtw_abi_version.restype = i32
     lib.rtw_abi_version.argtypes = []
+    lib.rtw_has_variants.restype = i32
+    lib.rtw_has_variants.argtypes = []
     lib.rtw_device_count.restype = i32
     lib.rtw_device_count.argtypes = [C.POINTER(i32)]
     lib.rtw_image_height.restype = i32

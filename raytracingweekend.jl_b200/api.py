@@ -281,6 +281,11 @@ def scene_load(path):
     return geom, mat, kind
 
 
+def has_variants() -> bool:
+    """True when librtw_b200.so was built with RTW_BUILD_VARIANTS=1 (the kernel families kept as measured comparisons)."""
+    return bool(_lib.load().rtw_has_variants())
+
+
 _default_renderer: Optional[Renderer] = None
 
 

@@ -7,10 +7,22 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false
        -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Xptxas -v)
-SRCS=(rtw_kernels rtw_fused2 rtw_f64 rtw_capi rtw_image rtw_wavefront rtw_cta_wavefront)
+SRCS=(rtw_kernels rtw_fused2 rtw_f64 rtw_capi rtw_image rtw_wavefront)
+# RTW_BUILD_VARIANTS=1: also build the kernel families kept only as measured comparisons (the first fused kernel with
+# its rays-per-lane / sweep variants, the CTA wavefront, 4 cooperating lanes, per-slot candidate walks); their tests are
+# marked `variants`.  The default library ships the default kernel, the split wavefront, the grid mode and Float64.
+OUT=librtw_b200.so
+OBJDIR=.
+if [ "${RTW_BUILD_VARIANTS:-0}" = "1" ]; then
+    FLAGS+=(-DRTW_BUILD_VARIANTS)
+    SRCS+=(rtw_cta_wavefront)
+    OUT=librtw_b200_variants.so   # select it with RTW_B200_LIB=<path>
+    OBJDIR=variants_obj
+    mkdir -p "$OBJDIR"
+fi
 pids=()
 for s in "${SRCS[@]}"; do
-    "$NVCC" "${FLAGS[@]}" -c "$s.cu" -o "$s.o" > "$s.log" 2>&1 &
+    "$NVCC" "${FLAGS[@]}" -c "$s.cu" -o "$OBJDIR/$s.o" > "$s.log" 2>&1 &
     pids+=($!)
 done
 rc=0
@@ -20,6 +32,7 @@ done
 [ $rc -eq 0 ] || exit 1
 cat ./*.log | grep -E "spill|registers" | sort | uniq -c | sort -rn | head -5 || true
 rm -f ./*.log
-OBJS=("${SRCS[@]/%/.o}")
-"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a "${OBJS[@]}" -o librtw_b200.so -lpthread -ldl
-echo "built $(pwd)/librtw_b200.so"
+OBJS=()
+for s in "${SRCS[@]}"; do OBJS+=("$OBJDIR/$s.o"); done
+"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a "${OBJS[@]}" -o "$OUT" -lpthread -ldl
+echo "built $(pwd)/$OUT"

@@ -131,6 +131,20 @@ constexpr int kDefaultSweep = RTW_SWEEP_PACKED;
 constexpr int kDefaultCoop = 2;
 constexpr int kDefaultTail = RTW_TAIL_UNIFIED;
 
+#ifdef RTW_BUILD_VARIANTS
+constexpr bool kHaveVariants = true;
+#else
+constexpr bool kHaveVariants = false;
+#endif
+
+// the default build ships one configuration of the fused kernel: unified tail, packed sweep, one path per lane, two
+// cooperating lanes, own-ray candidate walk (per-slot walk for streamed lists)
+bool variant_is_built(bool streamed, int rays, int sweep, int coop, int tail, int walk) {
+    if (kHaveVariants) return true;
+    if (tail != RTW_TAIL_UNIFIED || rays != 1 || sweep != RTW_SWEEP_PACKED || coop != 2) return false;
+    return streamed || walk == RTW_WALK_DEFAULT || walk == RTW_WALK_OWN_RAY;
+}
+
 int fail(rtw_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg;
     return code;
@@ -358,8 +372,10 @@ int enqueue_trace(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, i
                 p.rk[2 * r + 1] = p.key1 + r * rtw::kPhiloxW1;
             }
             RTW_CUDA(ctx, rtw::launch_fused_trace2_grid(p, ds.num_sms, ctx->blocks_per_sm, stream, &li));
+#ifdef RTW_BUILD_VARIANTS
         } else if (ctx->mode == RTW_MODE_CTA_WAVEFRONT && ctx->n_spheres <= rtw::kTileSpheres) {
             RTW_CUDA(ctx, rtw::launch_cta_wavefront_trace(p, ds.num_sms, ctx->blocks_per_sm, stream, &li));
+#endif
         } else if (ctx->mode == RTW_MODE_WAVEFRONT) {
             if (ctx->n_spheres > rtw::kTileSpheres)
                 return fail(ctx, RTW_E_UNSUPPORTED, "RTW_MODE_WAVEFRONT supports at most 1024 spheres; use RTW_MODE_FUSED");
@@ -373,6 +389,8 @@ int enqueue_trace(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, i
             const int coop = ctx->coop > 0 ? ctx->coop : kDefaultCoop;
             const int tail = ctx->tail > 0 ? ctx->tail : kDefaultTail;
             // the unified tail exists for the default sweep family: packed, one path per lane, 2 or 4 cooperating lanes
+            if (!variant_is_built(ctx->n_spheres > rtw::kTileSpheres, rays, sweep, coop, tail, ctx->walk))
+                return fail(ctx, RTW_E_UNSUPPORTED, "this kernel variant needs a library built with RTW_BUILD_VARIANTS=1");
             if (tail == RTW_TAIL_UNIFIED && rays == 1 && sweep == RTW_SWEEP_PACKED && (coop == 2 || coop == 4)) {
                 rc = grow(ctx, &ds.d_uv, &ds.uv_cap, (size_t)W + (size_t)H);
                 if (rc) return rc;
@@ -1014,6 +1032,8 @@ extern "C" {
 
 int rtw_abi_version(void) { return RTW_ABI_VERSION; }
 
+int rtw_has_variants(void) { return kHaveVariants ? 1 : 0; }
+
 int rtw_image_height(int image_width) {
     if (image_width < 0) return 0;
     return (int)(((long long)image_width * 9) / 16);  // image_width div (16//9), src/render.jl:11-12
@@ -1122,10 +1142,12 @@ int rtw_set_option(rtw_ctx* ctx, int option, int64_t value) {
         case RTW_OPT_MODE:
             if (value != RTW_MODE_FUSED && value != RTW_MODE_WAVEFRONT && value != RTW_MODE_CTA_WAVEFRONT && value != RTW_MODE_GRID)
                 return fail(ctx, RTW_E_INVALID_ARG, "unknown mode");
+            if (value == RTW_MODE_CTA_WAVEFRONT && !kHaveVariants)
+                return fail(ctx, RTW_E_UNSUPPORTED, "RTW_MODE_CTA_WAVEFRONT needs a library built with RTW_BUILD_VARIANTS=1");
             ctx->mode = (int)value;
             return RTW_OK;
         case RTW_OPT_STRIP:
-            return RTW_OK;  // accepted for ABI compatibility; paths are flushed individually since ABI v1
+            return fail(ctx, RTW_E_UNSUPPORTED, "RTW_OPT_STRIP was removed in ABI v3");
         case RTW_OPT_RAYS_PER_LANE:
             if (value != 0 && value != 1 && value != 2 && value != 4)
                 return fail(ctx, RTW_E_INVALID_ARG, "rays_per_lane must be 0 (default), 1, 2 or 4");

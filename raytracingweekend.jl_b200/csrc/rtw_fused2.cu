@@ -207,6 +207,75 @@ __device__ __forceinline__ void sweep_masks_packed2(uint32_t tile_lane, uint32_t
     }
 }
 
+// The sweep of the own-ray walk below: same tests and same mask words as sweep_masks_packed2, but
+//   * ONE summary word per lane, bit w = c*kCoop + q set when mask word (super-chunk c, slot q) holds a candidate -- the
+//     order in which the words sit in shared memory, so the walk derives both addresses from w with shifts;
+//   * the ragged last super-chunk runs the same number of pairs on every lane of a group (ceil(pairs / kCoop), the
+//     tile is zero-padded to a whole super-chunk), unrolled by 4; tests of pairs that do not exist are forced to "miss"
+//     when the mask word is stored.  Lists <= 32 * 32 spheres (kCoop * n_super_chunks <= 32 summary bits).
+template <int kCoop, int kBlock>
+__device__ __forceinline__ uint32_t sweep_masks_packed3(uint32_t tile_lane, uint32_t count, uint32_t coop_h,
+                                                        uint32_t mask_lane, const f3 (&o)[kCoop], const f3 (&d)[kCoop]) {
+    constexpr uint32_t kSuper = 32u * kCoop;
+    constexpr uint32_t kSuperPairs = 16u * kCoop;
+    const uint32_t npairs = (count + 1u) >> 1;
+    const uint32_t nfull = (count & 1u) ? (npairs - 1u) / kSuperPairs : npairs / kSuperPairs;
+    uint32_t summary = 0u;
+    uint32_t a = tile_lane, ma = mask_lane, bit = 1u;
+    for (uint32_t c = 0; c < nfull; ++c) {
+        uint32_t m[kCoop];
+#pragma unroll
+        for (int r = 0; r < kCoop; ++r) m[r] = 0u;
+        // coop 4: 8 pairs per unrolled body (the 16-pair body of 4 rays is ~15 KB of code), coop 2: all 16
+        constexpr int kBody = kCoop == 4 ? 8 : 16;
+#pragma unroll 1
+        for (int half = 0; half < 16 / kBody; ++half) {
+#pragma unroll
+            for (int i = 0; i < kBody; ++i)
+                test_pair_packed<kCoop>(lds128(a + (uint32_t)i * (kCoop * 32u)), lds128(a + (uint32_t)i * (kCoop * 32u) + 16u), o, d, m);
+            a += kBody * kCoop * 32u;
+        }
+#pragma unroll
+        for (int r = 0; r < kCoop; ++r) {
+            sts32(ma + (uint32_t)r * (kBlock * 4u), m[r]);
+            summary |= m[r] != 0xffffffffu ? (bit << r) : 0u;
+        }
+        ma += kCoop * kBlock * 4u;
+        bit <<= kCoop;
+    }
+    const uint32_t pairs_here = npairs - nfull * kSuperPairs;  // 0 .. kSuperPairs
+    if (pairs_here != 0u) {
+        uint32_t m[kCoop];
+#pragma unroll
+        for (int r = 0; r < kCoop; ++r) m[r] = 0u;
+        const uint32_t run = (pairs_here + kCoop - 1u) / kCoop;  // pairs every lane runs (uniform), 1 .. 16
+        uint32_t i = 0;
+        for (; i + 4u <= run; i += 4u) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                test_pair_packed<kCoop>(lds128(a + (uint32_t)u * (kCoop * 32u)), lds128(a + (uint32_t)u * (kCoop * 32u) + 16u), o, d, m);
+            a += 4u * kCoop * 32u;
+        }
+        for (; i < run; ++i) {
+            test_pair_packed<kCoop>(lds128(a), lds128(a + 16u), o, d, m);
+            a += kCoop * 32u;
+        }
+        // this lane's real tests: pairs coop_h, coop_h + kCoop, ... < pairs_here; the last of them may end in the pad
+        // partner of an odd last sphere.  Everything after them (zero pairs of the padding, the pad partner) = miss.
+        const uint32_t mine = pairs_here > coop_h ? (pairs_here - coop_h + kCoop - 1u) / kCoop : 0u;
+        const uint32_t real = 2u * mine - (((count & 1u) != 0u && mine != 0u && coop_h == (pairs_here - 1u) % kCoop) ? 1u : 0u);
+        const uint32_t sh = 32u - 2u * run;            // left-align the `2 * run` tests that were executed
+        const uint32_t fill = low_mask(32u - real);    // bits below the `real` top ones
+#pragma unroll
+        for (int r = 0; r < kCoop; ++r) {
+            m[r] = (sh >= 32u ? 0u : (m[r] << sh)) | fill;
+            sts32(ma + (uint32_t)r * (kBlock * 4u), m[r]);
+            summary |= m[r] != 0xffffffffu ? (bit << r) : 0u;
+        }
+    }
+    return summary;
+}
+
 // Candidate resolution, transposed: every lane walks ALL candidates of ITS OWN ray -- its own slot-0 mask words and
 // the slot-q words of its group partners lane^q, read straight from their shared-memory slices -- in one loop with
 // the ray in registers; no per-slot loops, no merge of partial results.  The candidates of a ray then arrive out of
@@ -223,29 +292,33 @@ __device__ __forceinline__ uint32_t perm_code_to_index(uint32_t code, uint32_t c
 
 template <int kCoop, int kBlock>
 __device__ __forceinline__ void walk_own_ray_perm(const float4* __restrict__ aos_perm, const uint32_t* s_mask_base,
-                                                  const f3 o, const f3 d, const bool alive,
-                                                  const uint32_t (&summary)[kCoop], float& best_t, int& best_k) {
+                                                  const f3 o, const f3 d, const bool alive, const uint32_t summary,
+                                                  float& best_t, int& best_k) {
     const float tmin = 1e-4f;  // T(1e-4), src/ray_color.jl:19
-    constexpr uint32_t kW = 32u / kCoop;  // summary bits (super-chunks) per slot: a list tile holds <= kW super-chunks
     const uint32_t tid = threadIdx.x, h = tid & (kCoop - 1);
     __syncwarp();  // the partners' mask words are visible
-    uint32_t sum = summary[0];
+    // summary bit w = c*kCoop + q of lane L says: L's mask word (c, slot q) -- the tests of the ray of lane L^q -- holds a
+    // candidate.  The words about MY ray are word (c, q) of lane L^q for q = 0 .. kCoop-1: pick, from each partner's
+    // summary, the bits of its slot q.
+    constexpr uint32_t kSlot0 = kCoop == 2 ? 0x55555555u : 0x11111111u;  // bits with w mod kCoop == 0
+    uint32_t sum = summary & kSlot0;
 #pragma unroll
-    for (int q = 1; q < kCoop; ++q) sum |= __shfl_xor_sync(kFullMask, summary[q], q) << (q * kW);
+    for (int q = 1; q < kCoop; ++q) sum |= __shfl_xor_sync(kFullMask, summary, q) & (kSlot0 << q);
     if (!alive) sum = 0u;
-    const uint32_t a_base = smem_u32(aos_perm), m_base = smem_u32(s_mask_base);
+    const uint32_t a_base = smem_u32(aos_perm) + 31u * 16u, m_base = smem_u32(s_mask_base) + tid * 4u;
     uint32_t cand = 0u, a31 = 0u, code31 = 0u;
     float bt = __int_as_float(0x7f800000);
     uint32_t bcode = 0xffffffffu;
     for (;;) {
         if (cand == 0u) {
             if (sum == 0u) break;
-            const uint32_t w = (uint32_t)__ffs((int)sum) - 1u;
+            const uint32_t w = (uint32_t)__ffs((int)sum) - 1u;  // = c*kCoop + q
             sum &= sum - 1u;
-            const uint32_t q = w / kW, c = w & (kW - 1u);
-            cand = ~lds32(m_base + ((c * kCoop + q) * kBlock + (tid ^ q)) * 4u);  // lane^q tested my ray in its slot q
-            code31 = (c * kCoop + (h ^ q)) * 32u + 31u;
-            a31 = a_base + code31 * 16u;
+            // lane^q tested my ray in its slot q: word index w of thread tid ^ q, q = w mod kCoop
+            cand = ~lds32((m_base + w * (kBlock * 4u)) ^ ((w & (kCoop - 1u)) << 2));
+            // it tested the spheres of ITS run: position code (c*kCoop + (h^q))*32 + j = ((w ^ h) << 5) + j
+            code31 = ((w ^ h) << 5) + 31u;
+            a31 = a_base + ((w ^ h) << 9);  // address of entry j = 31 of that run; test j = 31 - p sits 16*p below
         }
         const uint32_t p = bfind_u32(cand);
         cand &= low_mask(p);
@@ -366,11 +439,11 @@ __device__ __forceinline__ void merge_partial_hits(const float (&bt)[kCoop], con
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------
-template <bool kMulti, int kCoop, bool kOwnWalk, bool kGrid = false>
-__global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __grid_constant__ TraceParams P) {
+template <bool kMulti, int kCoop, bool kOwnWalk, bool kGrid = false, int kMinBlocks = 3, int kBlock = kTraceBlock>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) fused_trace2_kernel(const __grid_constant__ TraceParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_bar[2];
-    __shared__ __align__(16) uint4 s_coop[kTraceBlock / 32][32];  // rejection-sampling requests of a warp
+    __shared__ __align__(16) uint4 s_coop[kBlock / 32][32];  // rejection-sampling requests of a warp
     const uint32_t n = P.n_spheres;
     const float4* __restrict__ g_src = P.geom_pairs;
     const uint32_t n_stage = (n + 1u) & ~1u;
@@ -381,7 +454,7 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
     float4* s_tile1 = s_tile0 + tile_cap;  // kMulti: second streaming buffer; else: permuted AoS copy of the list
     uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tile0 + 2u * tile_cap) + threadIdx.x;
 
-    for (uint32_t i = threadIdx.x; i < 2u * tile_cap; i += kTraceBlock) s_tile0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t i = threadIdx.x; i < 2u * tile_cap; i += kBlock) s_tile0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (threadIdx.x == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
@@ -646,14 +719,14 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
             int bk[kCoop];
             uint32_t summary[kCoop];
             exchange_rays<kCoop>(o, d, alive, so, sd, sa);
-            if (!kMulti) {
-                sweep_masks_packed2<kCoop, kCoop, kTraceBlock>(smem_u32(s_tile0) + h * 32u, n, h, smem_u32(s_mask), so, sd,
+            if (!kMulti && kOwnWalk) {
+                const uint32_t sum1 = sweep_masks_packed3<kCoop, kBlock>(smem_u32(s_tile0) + h * 32u, n, h,
+                                                                              smem_u32(s_mask), so, sd);
+                walk_own_ray_perm<kCoop, kBlock>(s_tile1, s_mask - threadIdx.x, o, d, alive, sum1, best_t, best_k);
+            } else if (!kMulti) {
+                sweep_masks_packed2<kCoop, kCoop, kBlock>(smem_u32(s_tile0) + h * 32u, n, h, smem_u32(s_mask), so, sd,
                                                                summary);
-                if (kOwnWalk) {
-                    walk_own_ray_perm<kCoop, kTraceBlock>(s_tile1, s_mask - threadIdx.x, o, d, alive, summary, best_t, best_k);
-                } else {
-                    walk_candidates_perm<kCoop, kCoop, kTraceBlock>(s_tile1, h, s_mask, so, sd, sa, summary, bt, bk);
-                }
+                walk_candidates_perm<kCoop, kCoop, kBlock>(s_tile1, h, s_mask, so, sd, sa, summary, bt, bk);
             } else {
 #pragma unroll
                 for (int q = 0; q < kCoop; ++q) {
@@ -678,8 +751,8 @@ __global__ void __launch_bounds__(kTraceBlock, 3) fused_trace2_kernel(const __gr
                     const uint32_t tile_lane = smem_u32((t & 1u) ? s_tile1 : s_tile0) + h * 32u;
                     if (t & 1u) { mbar_wait(&s_bar[1], bar_phase1); bar_phase1 ^= 1u; }
                     else { mbar_wait(&s_bar[0], bar_phase0); bar_phase0 ^= 1u; }
-                    sweep_masks_packed2<kCoop, kCoop, kTraceBlock>(tile_lane, cnt, h, smem_u32(s_mask), so, sd, summary);
-                    walk_candidates_pairs<kCoop, kCoop, kTraceBlock>(tile_lane, h, smem_u32(s_mask), base, so, sd, sa,
+                    sweep_masks_packed2<kCoop, kCoop, kBlock>(tile_lane, cnt, h, smem_u32(s_mask), so, sd, summary);
+                    walk_candidates_pairs<kCoop, kCoop, kBlock>(tile_lane, h, smem_u32(s_mask), base, so, sd, sa,
                                                                      summary, bt, bk);
                     __syncthreads();  // the buffer may be overwritten by the prefetch issued in the next iteration
                 }
@@ -703,30 +776,30 @@ __global__ void __launch_bounds__(256) uv_table_kernel(int W, int H, float* __re
     if (t < H) v_tab[t] = __fdiv_rn((float)(H - 1 - t), (float)H);
 }
 
-template <bool kMulti, int kCoop, bool kOwnWalk>
+template <bool kMulti, int kCoop, bool kOwnWalk, int kMinBlocks = 3, int kBlock = kTraceBlock>
 cudaError_t launch_variant2(const TraceParams& p, int num_sms, int blocks_per_sm_override, cudaStream_t stream,
                             LaunchInfo* info) {
-    auto kern = fused_trace2_kernel<kMulti, kCoop, kOwnWalk>;
+    auto kern = fused_trace2_kernel<kMulti, kCoop, kOwnWalk, false, kMinBlocks, kBlock>;
     constexpr uint32_t kGran = 32u * kCoop;
     const uint32_t tile_cap = kMulti ? kTileSpheres : ((p.n_spheres + kGran - 1u) / kGran) * kGran;
     const uint32_t chunks = tile_cap / 32u;  // mask words per lane: (tile_cap / kGran) super-chunks x kCoop slots
-    const int smem = (int)(2u * tile_cap * 16u + chunks * kTraceBlock * 4u);
+    const int smem = (int)(2u * tile_cap * 16u + chunks * kBlock * 4u);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTraceBlock, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     if (blocks_per_sm_override > 0 && blocks_per_sm_override < per_sm) per_sm = blocks_per_sm_override;
     long long grid = (long long)num_sms * per_sm;  // persistent grid: every CTA is resident
-    const long long max_useful = (long long)((p.n_paths + (unsigned long long)kTraceBlock - 1ull) /
-                                             (unsigned long long)kTraceBlock);
+    const long long max_useful = (long long)((p.n_paths + (unsigned long long)kBlock - 1ull) /
+                                             (unsigned long long)kBlock);
     if (grid > max_useful) grid = max_useful;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, kTraceBlock, smem, stream>>>(p);
+    kern<<<(unsigned)grid, kBlock, smem, stream>>>(p);
     if (info) {
         info->grid = (int)grid;
-        info->block = kTraceBlock;
+        info->block = kBlock;
         info->smem_bytes = smem;
         info->blocks_per_sm = per_sm;
         info->launches = 1;
@@ -785,17 +858,24 @@ cudaError_t launch_fused_trace2_grid(const TraceParams& p, int num_sms, int bloc
 cudaError_t launch_fused_trace2(const TraceParams& p, int num_sms, int blocks_per_sm_override, int coop, int walk,
                                 cudaStream_t stream, LaunchInfo* info) {
     const bool multi = p.n_spheres > kTileSpheres;
-    if (multi) {
-        return coop == 4 ? launch_variant2<true, 4, false>(p, num_sms, blocks_per_sm_override, stream, info)
-                         : launch_variant2<true, 2, false>(p, num_sms, blocks_per_sm_override, stream, info);
-    }
-    if (walk == 0) walk = coop == 4 ? 2 : 1;  // measured: per-slot walks win with 2 cooperating lanes, own-ray with 4
+    // the shipped configuration: 2 cooperating lanes; single-tile lists resolve candidates with the own-ray walk,
+    // streamed lists (> 1024 spheres) tile by tile with the per-slot walk
+    if (coop == 0) coop = 2;
+    if (walk == 0) walk = 2;  // measured (profiles/r02_summary.md): own-ray walk wins with 2 and with 4 lanes
+    if (multi && coop == 2) return launch_variant2<true, 2, false>(p, num_sms, blocks_per_sm_override, stream, info);
+    if (!multi && coop == 2 && walk == 2) return launch_variant2<false, 2, true>(p, num_sms, blocks_per_sm_override, stream, info);
+#ifdef RTW_BUILD_VARIANTS
+    if (multi) return launch_variant2<true, 4, false>(p, num_sms, blocks_per_sm_override, stream, info);
     if (walk == 1) {  // per-slot candidate walks + merge
         return coop == 4 ? launch_variant2<false, 4, false>(p, num_sms, blocks_per_sm_override, stream, info)
                          : launch_variant2<false, 2, false>(p, num_sms, blocks_per_sm_override, stream, info);
     }
-    return coop == 4 ? launch_variant2<false, 4, true>(p, num_sms, blocks_per_sm_override, stream, info)
-                     : launch_variant2<false, 2, true>(p, num_sms, blocks_per_sm_override, stream, info);
+    if (blocks_per_sm_override == 2)  // 128 registers per thread, 2 CTAs per SM
+        return launch_variant2<false, 4, true, 2>(p, num_sms, blocks_per_sm_override, stream, info);
+    return launch_variant2<false, 4, true>(p, num_sms, blocks_per_sm_override, stream, info);
+#else
+    return cudaErrorNotSupported;  // built without RTW_BUILD_VARIANTS=1
+#endif
 }
 
 }  // namespace rtw

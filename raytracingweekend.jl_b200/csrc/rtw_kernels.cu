@@ -18,6 +18,7 @@ namespace rtw {
 
 namespace {
 
+#ifdef RTW_BUILD_VARIANTS  // the first fused kernel family (RTW_TAIL_SPLIT): measured comparison, not shipped by default
 // ---- the persistent fused kernel ------------------------------------------------------------------------------
 // kMulti = false: the whole list (<= kTileSpheres) is staged once; warps then run free of CTA barriers.
 // kMulti = true : the list is streamed per bounce through two 16 KB TMA buffers, CTA-synchronously.
@@ -231,6 +232,8 @@ __global__ void __launch_bounds__(kTraceBlock, (R == 1 ? 3 : (R == 2 ? 2 : 1)))
     if (lane == 0 && seg_count) atomicAdd(P.counters + 1, (unsigned long long)seg_count);
 }
 
+#endif  // RTW_BUILD_VARIANTS
+
 // ---- resolve: accum / n_samples -> sqrt -> Float32 (src/render.jl:40, src/vec.jl:22) ------------------------
 __global__ void __launch_bounds__(256) resolve_kernel(const unsigned long long* __restrict__ accum, int W, int H,
                                                       int n_rows, int row_start, int row_stride, int spp,
@@ -383,6 +386,7 @@ __global__ void __launch_bounds__((kMixSweepWarps + kOtherWarps) * 32)
 
 namespace {
 
+#ifdef RTW_BUILD_VARIANTS
 template <int R, int SWEEP, bool kMulti, int kCoop>
 cudaError_t launch_trace_variant(const TraceParams& p, int num_sms, int blocks_per_sm_override, cudaStream_t stream,
                                  LaunchInfo* info) {
@@ -434,10 +438,16 @@ cudaError_t launch_trace_rays(const TraceParams& p, int num_sms, int bps, int R,
     }
 }
 
+#endif  // RTW_BUILD_VARIANTS
+
 }  // namespace
 
 cudaError_t launch_fused_trace(const TraceParams& p, int num_sms, int blocks_per_sm_override, int rays_per_lane,
                                int sweep, int coop, cudaStream_t stream, LaunchInfo* info) {
+#ifndef RTW_BUILD_VARIANTS
+    (void)p; (void)num_sms; (void)blocks_per_sm_override; (void)rays_per_lane; (void)sweep; (void)coop; (void)stream; (void)info;
+    return cudaErrorNotSupported;  // built without RTW_BUILD_VARIANTS=1
+#else
     if (sweep != kSweepBranch && sweep != kSweepMask && rays_per_lane == 1 && coop > 1) {
         if (coop == 2) return launch_trace_tiles<1, kSweepPacked, 2>(p, num_sms, blocks_per_sm_override, stream, info);
         return launch_trace_tiles<1, kSweepPacked, 4>(p, num_sms, blocks_per_sm_override, stream, info);
@@ -445,6 +455,7 @@ cudaError_t launch_fused_trace(const TraceParams& p, int num_sms, int blocks_per
     if (sweep == kSweepBranch) return launch_trace_rays<kSweepBranch>(p, num_sms, blocks_per_sm_override, rays_per_lane, stream, info);
     if (sweep == kSweepMask) return launch_trace_rays<kSweepMask>(p, num_sms, blocks_per_sm_override, rays_per_lane, stream, info);
     return launch_trace_rays<kSweepPacked>(p, num_sms, blocks_per_sm_override, rays_per_lane, stream, info);
+#endif
 }
 
 cudaError_t launch_resolve(const unsigned long long* accum, int W, int H, int n_rows, int row_start, int row_stride,

@@ -12,6 +12,21 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1e-3  # per-channel L-infinity, Float32 image after gamma (north_star)
 
+NEEDS_VARIANTS = "kernel variant kept as a measured comparison: needs a library built with RTW_BUILD_VARIANTS=1"
+
+
+def _built(rtw, rays=0, sweep=0, coop=0, tail=0, walk=0, mode=0, n=0):
+    """Does the loaded library contain this kernel configuration?  The default build ships ONE configuration of the
+    fused kernel (unified tail, packed sweep, 1 path per lane, 2 cooperating lanes, own-ray walk), the split wavefront,
+    the grid mode and Float64; everything else is compiled only with RTW_BUILD_VARIANTS=1 (csrc/build.sh)."""
+    if rtw.has_variants():
+        return True
+    if mode == rtw.RTW_MODE_CTA_WAVEFRONT:
+        return False
+    if mode in (rtw.RTW_MODE_WAVEFRONT, rtw.RTW_MODE_GRID):
+        return True  # these modes take no kernel options
+    return rays in (0, 1) and sweep in (0, 3) and coop in (0, 2) and tail in (0, 2) and (walk in (0, 2) or n > 1024)
+
 
 def _compare(img_gpu, img_cpu, max_mismatch_frac=1e-3):
     assert img_gpu.shape == img_cpu.shape and img_gpu.dtype == np.float32
@@ -27,9 +42,12 @@ def _compare(img_gpu, img_cpu, max_mismatch_frac=1e-3):
 
 @pytest.mark.parametrize("rays,sweep,coop,tail", [(1, 1, 1, 1), (2, 1, 1, 1), (1, 2, 1, 1), (2, 2, 1, 1), (4, 2, 1, 1),
                                                   (1, 3, 1, 1), (2, 3, 1, 1), (4, 3, 1, 1), (1, 3, 2, 1), (1, 3, 4, 1),
-                                                  (1, 3, 2, 2), (1, 3, 4, 2)])
+                                                  (1, 3, 2, 2), (1, 3, 4, 2), (0, 0, 0, 0)])
 def test_cfg1_scene_2_spheres_all_variants(rtw, oracle, renderer, scenes, rays, sweep, coop, tail):
     # BASELINE configs[0]: scene_2_spheres, 96x54, 16 spp, 4 bounces, Float32 (test/runtests.jl:194 shape)
+    # (0, 0, 0, 0) = the library defaults = the shipped configuration
+    if not _built(rtw, rays, sweep, coop, tail):
+        pytest.skip(NEEDS_VARIANTS)
     g, m, k = scenes["two"]
     cam = rtw.t_default_cam()
     renderer.set_option(rtw.RTW_OPT_RAYS_PER_LANE, rays)
@@ -57,6 +75,8 @@ def test_random_spheres_coop_variants_identical(rtw, oracle, renderer, scenes, c
     # the lane-cooperative sweep merges per-lane partial closest hits: same image bits as the oracle on the
     # 484-sphere scene (odd super-chunk tails, ties, inside hits); tail 1 = per-state shading/regeneration,
     # tail 2 = unified Philox block + cooperative rejection sampling (rtw_fused2.cu)
+    if not _built(rtw, coop=coop, tail=tail):
+        pytest.skip(NEEDS_VARIANTS)
     g, m, k = scenes["random"]
     cam = rtw.t_cam1()
     renderer.set_option(rtw.RTW_OPT_COOP, coop)
@@ -103,6 +123,8 @@ def test_tail_variants_on_reference_scenes_and_odd_shapes(rtw, oracle, renderer,
     # both tails of the fused kernel on: the dielectric scenes (coin flips, total internal reflection, hollow bubble),
     # the depth-of-field camera (disk rejection), 1 spp (un-jittered sample only; division by 1), odd widths
     # (multiply-shift division by W), deep paths and a 3-row tile split
+    if not _built(rtw, tail=tail):
+        pytest.skip(NEEDS_VARIANTS)
     renderer.set_option(rtw.RTW_OPT_TAIL, tail)
     try:
         for name, cam, W, spp, depth, seed in [("diel", rtw.t_cam2(), 160, 32, 16, 7), ("bubble", rtw.t_default_cam(), 131, 9, 50, 2),
@@ -121,6 +143,8 @@ def test_candidate_walk_variants(rtw, oracle, renderer, scenes, coop, walk):
     # RTW_WALK_SLOTS: per-slot walks in list order + merge; RTW_WALK_OWN_RAY: each lane resolves its own ray from its
     # partners' masks, closest hit in order-independent form (min t, ties to the larger list index).  Same bits on the
     # random scene, on coincident spheres (ties across cooperating lanes) and on ragged list sizes.
+    if not _built(rtw, coop=coop, walk=walk):
+        pytest.skip(NEEDS_VARIANTS)
     g, m, k = scenes["random"]
     tie_geom = np.array([[0, 0, -1, 0.5]] * 7 + [[0, -100.5, -1, 100]], np.float32)
     tie_mat = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [1, 1, 0, 0], [0, 1, 1, 0], [1, 0, 1, 0], [0.2, 0.9, 0.4, 0],
@@ -201,6 +225,8 @@ def test_large_list_streams_through_tma_tiles(rtw, oracle, renderer):
     cam = rtw.t_cam1()
     for rays, sweep, coop, tail in [(1, 3, 2, 2), (1, 3, 4, 2), (1, 3, 2, 1), (1, 3, 4, 1), (1, 3, 1, 1), (2, 3, 1, 1), (2, 2, 1, 1),
                                     (1, 1, 1, 1)]:
+        if not _built(rtw, rays, sweep, coop, tail, n=len(scene[2])):
+            continue
         renderer.set_option(rtw.RTW_OPT_RAYS_PER_LANE, rays)
         renderer.set_option(rtw.RTW_OPT_SWEEP, sweep)
         renderer.set_option(rtw.RTW_OPT_COOP, coop)
@@ -319,11 +345,12 @@ def test_wavefront_mode_matches_fused_and_oracle(rtw, oracle, scenes):
             r.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_FUSED)
             a = np.array(r.render(cam, W, spp, max_depth=depth, seed=5))
             sa = dict(r.last_stats)
-            r.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_CTA_WAVEFRONT)
-            c = np.array(r.render(cam, W, spp, max_depth=depth, seed=5))
-            sc = dict(r.last_stats)
-            assert np.array_equal(a, c), name + " (CTA wavefront)"
-            assert sa["ray_segments"] == sc["ray_segments"]
+            if _built(rtw, mode=rtw.RTW_MODE_CTA_WAVEFRONT):
+                r.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_CTA_WAVEFRONT)
+                c = np.array(r.render(cam, W, spp, max_depth=depth, seed=5))
+                sc = dict(r.last_stats)
+                assert np.array_equal(a, c), name + " (CTA wavefront)"
+                assert sa["ray_segments"] == sc["ray_segments"]
             r.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_WAVEFRONT)
             b = np.array(r.render(cam, W, spp, max_depth=depth, seed=5))
             sb = dict(r.last_stats)
@@ -359,6 +386,8 @@ def test_ragged_list_sizes_all_sweeps(rtw, oracle, renderer, n):
     if n <= 1024:
         variants += [(1, 3, 2, 1, S), (1, 3, 2, 2, S)]  # split wavefront and CTA wavefront keep the list in one tile
     for rays, sweep, coop, mode, tail in variants:
+        if not _built(rtw, rays, sweep, coop, tail, mode=mode, n=n):
+            continue
         renderer.set_option(rtw.RTW_OPT_RAYS_PER_LANE, rays)
         renderer.set_option(rtw.RTW_OPT_SWEEP, sweep)
         renderer.set_option(rtw.RTW_OPT_COOP, coop)
@@ -432,8 +461,10 @@ def test_progressive_passes_checkpoint_and_rgb8(rtw, oracle, renderer, scenes, t
         renderer.resolve()
 
 
-@pytest.mark.parametrize("mode,tail", [(0, 1), (0, 2), (1, 0), (2, 0)])
+@pytest.mark.parametrize("mode,tail", [(0, 1), (0, 2), (1, 0), (2, 0), (3, 0)])
 def test_progressive_passes_in_every_mode(rtw, renderer, scenes, mode, tail):
+    if not _built(rtw, tail=tail, mode=mode):
+        pytest.skip(NEEDS_VARIANTS)
     cam = rtw.t_default_cam()
     renderer.set_scene(scenes["bubble"])
     renderer.set_option(rtw.RTW_OPT_MODE, mode)
@@ -657,6 +688,8 @@ def _random_soup(rtw, rng, trial):
 def test_random_sphere_soups_against_the_oracle(rtw, oracle, renderer, coop, tail, walk, mode):
     # the adversarial lists of the grid test (tiny / nested / hollow spheres, glass-heavy, axis-aligned rays, cameras
     # inside the cloud) through the kernel families, against the CPU oracle: same paths, segment for segment
+    if not _built(rtw, coop=coop, tail=tail, walk=walk, mode=mode):
+        pytest.skip(NEEDS_VARIANTS)
     rng = np.random.default_rng(1234)
     for opt, v in ((rtw.RTW_OPT_COOP, coop), (rtw.RTW_OPT_TAIL, tail), (rtw.RTW_OPT_WALK, walk), (rtw.RTW_OPT_MODE, mode)):
         renderer.set_option(opt, v)

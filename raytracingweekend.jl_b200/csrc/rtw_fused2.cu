@@ -327,21 +327,17 @@ __device__ __forceinline__ void walk_own_ray_perm(const float4* __restrict__ aos
         const float ocx = o.x - s.x, ocy = o.y - s.y, ocz = o.z - s.z;
         const float hb = fmaf(ocz, d.z, fmaf(ocy, d.y, ocx * d.x));
         const float cq = fmaf(-s.w, s.w, fmaf(ocz, ocz, fmaf(ocy, ocy, ocx * ocx)));
-        // Sphere entirely behind the origin (half_b > 0 and origin outside): sqrt(disc) <= half_b in IEEE
-        // arithmetic, so both roots are <= 0 < tmin and src/hit.jl:24-28 rejects them -- skip the square root.
-        if (hb > 0.0f && cq > 0.0f) continue;
+        // branch-free: a sphere wholly behind the origin has both roots <= 0 < tmin and falls out at `t >= tmin`
         const float sq = __fsqrt_rn(fmaf(hb, hb, -cq));
         const float r1 = -hb - sq, r2 = -hb + sq;  // src/hit.jl:23, 25
         const float t = r1 < tmin ? r2 : r1;       // the first root >= tmin, if any
-        if (t < tmin) continue;
         const uint32_t code = code31 - p;
-        if (t < bt) {
-            bt = t;
-            bcode = code;
-        } else if (t == bt && bcode != 0xffffffffu &&
-                   perm_code_to_index(code, kCoop) > perm_code_to_index(bcode, kCoop)) {
-            bcode = code;
+        if (t == bt && t >= tmin && bcode != 0xffffffffu) {  // rare: coincident surfaces -- the larger list index wins
+            if (perm_code_to_index(code, kCoop) > perm_code_to_index(bcode, kCoop)) bcode = code;
         }
+        const bool closer = t >= tmin && t < bt;
+        bt = closer ? t : bt;
+        bcode = closer ? code : bcode;
     }
     __syncwarp();  // all reads of the partners' mask words are done before the next sweep overwrites them
     best_t = bt;

@@ -543,6 +543,7 @@ def run_extras(args, R, r, scene, cam, stream, timed_steps, one_step_resident, n
         g_ms, g_segs, _ = timed_steps(lambda: (one_step_resident(), None)[1], 2)
         out["grid_mode"] = {"value": g_segs / (sum(g_ms) * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": sum(g_ms) / 2, "steps": 2,
                             "grid_fallback_rays_per_step": r.stats().get("grid_fallback_rays"),
+                            "grid_loose_cells_per_step": r.stats().get("grid_loose_cells"),
                             "note": "RTW_MODE_GRID: uniform-grid traversal instead of the linear sweep, bit-identical image; "
                                     "not the benchmarked path (no linear-sweep roofline applies)"}
     except Exception as e:  # the headline must not depend on the optional mode
@@ -571,6 +572,7 @@ def run_extras(args, R, r, scene, cam, stream, timed_steps, one_step_resident, n
         out["cfg5_grid"] = {"value": segs5 / (sum(ms5) * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": sum(ms5) / 2, "steps": 2,
                             "n_spheres": len(big[2]), "spp": 256, "scene_generation_s": t_gen, "scene_generator": gen,
                             "grid_fallback_rays_per_step": st5.get("grid_fallback_rays"),
+                            "grid_loose_cells_per_step": st5.get("grid_loose_cells"),
                             "equivalent_linear_sweep_T_instr_s": segs5 / 2 * len(big[2]) * FP32_INSTR_PER_TEST / (sum(ms5) / 2 * 1e-3) / 1e12,
                             "workload": f"BASELINE configs[4]: {len(big[2])} spheres, {W}x{R.image_height(W)}, 256 spp, depth {depth}, RTW_MODE_GRID"}
     except Exception as e:

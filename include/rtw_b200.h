@@ -85,8 +85,9 @@ typedef struct rtw_stats {
     /* ABI v3 */
     int32_t n_devices;       /* devices the call ran on (rows r -> device r mod n_devices)                 */
     int32_t reserved0;
-    uint64_t grid_fallback_rays; /* RTW_MODE_GRID: ray segments the traversal could not answer exactly and that
-                                    were resolved by the exact whole-list sweep (0 in the other modes)         */
+    uint64_t grid_fallback_rays; /* RTW_MODE_GRID: ray segments no registration margin covers (non-unit direction after
+                                    a glass reflection, flying far), resolved by the exact whole-list sweep     */
+    uint64_t grid_loose_cells;   /* RTW_MODE_GRID: cells walked with the loose registration (far part of long flights) */
 } rtw_stats;
 
 typedef struct rtw_ctx rtw_ctx;

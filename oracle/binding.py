@@ -221,6 +221,26 @@ def render(geom4, mat4, kind, cam_array, image_width, n_samples, *, max_depth=16
     return out.transpose(1, 0, 2), (lin.transpose(1, 0, 2) if lin is not None else None), stats
 
 
+def path_trace(geom4, mat4, kind, cam_array, image_width, i0, j0, s0, *, max_depth=16, seed=1):
+    """Debugging aid: the segments of one path -- rows of (origin xyz, direction xyz, closest sphere or -1, t)."""
+    lib = load()
+    geom = np.ascontiguousarray(geom4, dtype=np.float32).reshape(-1, 4)
+    mat = np.ascontiguousarray(mat4, dtype=np.float32).reshape(-1, 4)
+    knd = np.ascontiguousarray(kind, dtype=np.uint32).reshape(-1)
+    cam = _cam_struct(cam_array)
+    rgb = (C.c_double * 3)()
+    trace = np.zeros((max_depth + 1, 8), dtype=np.float64)
+    n = C.c_int()
+    fp = C.POINTER(C.c_float)
+    lib.rtwo_path_trace_f32.argtypes = [fp, fp, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(rtwo_camera_f32), C.c_int, C.c_int,
+                                        C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                        C.c_int, C.POINTER(C.c_int)]
+    lib.rtwo_path_trace_f32(geom.ctypes.data_as(fp), mat.ctypes.data_as(fp), knd.ctypes.data_as(C.POINTER(C.c_uint32)),
+                            len(knd), C.byref(cam), int(image_width), int(max_depth), int(seed), int(i0), int(j0), int(s0),
+                            rgb, trace.ctypes.data_as(C.POINTER(C.c_double)), len(trace), C.byref(n))
+    return np.array(list(rgb)), trace[:n.value]
+
+
 def path(geom4, mat4, kind, cam_array, image_width, i0, j0, s0, *, max_depth=16, seed=1):
     lib = load()
     geom = np.ascontiguousarray(geom4, dtype=np.float32).reshape(-1, 4)

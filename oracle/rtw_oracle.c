@@ -264,10 +264,24 @@ static cam_f64 load_cam_f64(const rtwo_camera_f64* c) {
     return k;
 }
 
+void rtwo_path_trace_f32(const float* geom4, const float* mat4, const uint32_t* kind, uint32_t n_spheres,
+                         const rtwo_camera_f32* cam, int image_width, int max_depth, uint64_t seed, int i0, int j0, int s0,
+                         double rgb[3], double* trace, int trace_cap, int* trace_n) {
+    world_f32 w = {geom4, mat4, kind, n_spheres, 0, 0, trace, trace_cap, 0};
+    cam_f32 c = load_cam_f32(cam);
+    int H = rtwo_image_height(image_width);
+    rtwo_rng g;
+    memset(&g, 0, sizeof g);
+    g.mode = RTWO_RNG_PHILOX;
+    rtwo_rng_begin_path(&g, seed, (uint32_t)(i0 * image_width + j0), (uint32_t)s0);
+    sample_path_f32(&w, &g, &c, image_width, H, max_depth, i0 + 1, j0 + 1, s0 + 1, rgb);
+    if (trace_n) *trace_n = w.trace_n;
+}
+
 void rtwo_path_f32(const float* geom4, const float* mat4, const uint32_t* kind, uint32_t n_spheres,
                    const rtwo_camera_f32* cam, int image_width, int max_depth, uint64_t seed, int i0, int j0, int s0,
                    double rgb[3], uint32_t* segments) {
-    world_f32 w = {geom4, mat4, kind, n_spheres, 0, 0};
+    world_f32 w = {geom4, mat4, kind, n_spheres, 0, 0, NULL, 0, 0};
     cam_f32 c = load_cam_f32(cam);
     int H = rtwo_image_height(image_width);
     rtwo_rng g;

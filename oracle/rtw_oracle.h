@@ -111,6 +111,11 @@ void rtwo_xoroshiro_u64(uint64_t seed, int n, uint64_t* out);
 void rtwo_xoroshiro_f32(uint64_t seed, int n, float* out);
 
 /* one path, by explicit (row i0, col j0, sample s0), 0-based; linear colour (Float64) out */
+/* debugging aid: the same path, with every segment recorded -- 8 doubles each: origin, direction, index of the
+ * closest sphere (-1 = miss), its t */
+void rtwo_path_trace_f32(const float* geom4, const float* mat4, const uint32_t* kind, uint32_t n_spheres,
+                         const rtwo_camera_f32* cam, int image_width, int max_depth, uint64_t seed, int i0, int j0, int s0,
+                         double rgb[3], double* trace, int trace_cap, int* trace_n);
 void rtwo_path_f32(const float* geom4, const float* mat4, const uint32_t* kind, uint32_t n_spheres,
                    const rtwo_camera_f32* cam, int image_width, int max_depth, uint64_t seed,
                    int i0, int j0, int s0, double rgb[3], uint32_t* segments);

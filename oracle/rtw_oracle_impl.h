@@ -134,6 +134,10 @@ typedef struct {
     uint32_t n;
     uint64_t segments;
     uint64_t tests;
+    /* optional debugging record of a single path (rtwo_path_trace_*): 8 doubles per segment -- origin, direction, index
+     * of the closest sphere (-1: miss), its t */
+    double* trace;
+    int trace_cap, trace_n;
 } SFX(world);
 
 /* hit(hittables::HittableList, r, tmin, tmax), src/hit.jl:38-50 */
@@ -152,6 +156,12 @@ static inline int SFX(hit_list)(SFX(world)* w, SFX(v3) o, SFX(v3) d, RT tmin, RT
     }
     w->segments += 1;
     w->tests += w->n;
+    if (w->trace && w->trace_n < w->trace_cap) {
+        double* r = w->trace + 8 * (size_t)w->trace_n++;
+        r[0] = o.x; r[1] = o.y; r[2] = o.z; r[3] = d.x; r[4] = d.y; r[5] = d.z;
+        r[6] = any ? (double)best->index : -1.0;
+        r[7] = any ? (double)best->t : 0.0;
+    }
     return any;
 }
 
@@ -299,7 +309,7 @@ static void SFX(render_row)(SFX(job)* jb, SFX(world)* w, rtwo_rng* g, int i0) {
 
 static void* SFX(worker)(void* arg) {
     SFX(job)* jb = (SFX(job)*)arg;
-    SFX(world) w = {jb->geom4, jb->mat4, jb->kind, jb->n, 0, 0};
+    SFX(world) w = {jb->geom4, jb->mat4, jb->kind, jb->n, 0, 0, NULL, 0, 0};
     rtwo_rng g;
     /* rows this call renders: r_k = row_start + k*row_stride, k = 0..nrows-1 */
     int nrows = (jb->H - jb->row_start + jb->row_stride - 1) / jb->row_stride;

@@ -143,6 +143,7 @@ class rtw_stats(C.Structure):
         ("n_devices", C.c_int32),
         ("reserved0", C.c_int32),
         ("grid_fallback_rays", C.c_uint64),
+        ("grid_loose_cells", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:

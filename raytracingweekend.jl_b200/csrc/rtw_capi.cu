@@ -34,10 +34,14 @@ struct DeviceState {
     uint32_t* d_kind = nullptr;
     size_t scene_cap = 0;
     // RTW_MODE_GRID: uniform grid over the scene (same content on every device)
-    uint32_t* d_grid_start = nullptr;
-    uint32_t* d_grid_items = nullptr;
+    uint32_t* d_grid_start[2] = {nullptr, nullptr};  // [0] tight, [1] loose registration
+    uint32_t* d_grid_items[2] = {nullptr, nullptr};
+    size_t grid_start_cap[2] = {0, 0}, grid_items_cap[2] = {0, 0};
     uint32_t* d_grid_big = nullptr;
-    size_t grid_start_cap = 0, grid_items_cap = 0, grid_big_cap = 0;
+    size_t grid_big_cap = 0;
+    uint32_t* d_cull_start = nullptr;
+    uint32_t* d_cull_items = nullptr;
+    size_t cull_start_cap = 0, cull_items_cap = 0;
     // Float64 scene and image buffers (rtw_*_f64)
     double4* d_geom64 = nullptr;
     double4* d_mat64 = nullptr;
@@ -95,6 +99,7 @@ struct rtw_ctx {
     uint32_t n_spheres64 = 0;
     bool have_scene64 = false;
     rtw::GridParams grid = {};  // host copy of the grid header (device pointers are per device)
+    bool grid_two = false;      // the loose registration has lists of its own (large scenes)
     bool grid_valid = false;    // the grid of the current scene has been built and uploaded (lazily: RTW_MODE_GRID only)
     std::vector<float> h_geom;  // host copy of geom4, kept for the lazy grid build
     float max_albedo = 0.f;     // largest albedo component of the scene (fixed-point head-room check)
@@ -356,9 +361,13 @@ int enqueue_trace(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, i
             if (rc) return rc;
             RTW_CUDA(ctx, cudaSetDevice(ds.device));
             p.grid = ctx->grid;
-            p.grid.cell_start = ds.d_grid_start;
-            p.grid.items = ds.d_grid_items;
             p.grid.big = ds.d_grid_big;
+            p.grid.cull.cell_start = ds.d_cull_start;
+            p.grid.cull.items = ds.d_cull_items;
+            p.grid.cell_start_tight = ds.d_grid_start[0];
+            p.grid.items_tight = ds.d_grid_items[0];
+            p.grid.cell_start_loose = ds.d_grid_start[ctx->grid_two ? 1 : 0];
+            p.grid.items_loose = ds.d_grid_items[ctx->grid_two ? 1 : 0];
             rc = grow(ctx, &ds.d_uv, &ds.uv_cap, (size_t)W + (size_t)H);
             if (rc) return rc;
             RTW_CUDA(ctx, rtw::launch_uv_tables(W, H, ds.d_uv, ds.d_uv + W, stream));
@@ -449,6 +458,7 @@ int enqueue_rows(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, in
 int finish_stats(rtw_ctx* ctx, DeviceState& ds, bool timing) {
     ds.last.ray_segments = ds.h_counters[1];
     ds.last.grid_fallback_rays = ds.h_counters[2];
+    ds.last.grid_loose_cells = ds.h_counters[3];
     ds.last.sphere_tests = ds.last.ray_segments * (uint64_t)ctx->n_spheres;
     if (timing && ds.last.rows_rendered > 0) {
         float a = 0.f, b = 0.f;
@@ -464,7 +474,8 @@ int finish_stats(rtw_ctx* ctx, DeviceState& ds, bool timing) {
 // RTW_MODE_GRID: bin the spheres (rtw_grid.cuh describes the structure and why the result is unchanged)
 struct HostGrid {
     rtw::GridParams hdr = {};
-    std::vector<uint32_t> cell_start, items, big;
+    std::vector<uint32_t> cell_start[2], items[2], big;  // [0] tight, [1] loose (empty: the same as tight)
+    std::vector<uint32_t> cull_start, cull_items;  // GridCull (long lists only)
 };
 
 void build_grid(const float* geom4, uint32_t n, HostGrid* out) {
@@ -516,49 +527,104 @@ void build_grid(const float* geom4, uint32_t n, HostGrid* out) {
             return;
         }
     }
-    const double inflate = 0.05 * h;  // registration margin: rounding of the traversal AND the reference's a = 1 shortcut
-    double r_min = 1e300;
-    for (uint32_t i : small) r_min = std::min(r_min, (double)radii[i]);
-    g.hdr.safe2 = (float)(0.5 * ((r_min + inflate) * (r_min + inflate) - r_min * r_min));  // half of it: slack for rounding
-    g.hdr.h = (float)h;
-    g.hdr.inv_h = 1.0f / g.hdr.h;
-    g.hdr.ox = (float)(lo[0] - 0.5 * h);
-    g.hdr.oy = (float)(lo[1] - 0.5 * h);
-    g.hdr.oz = (float)(lo[2] - 0.5 * h);
-    g.hdr.nx = nd[0]; g.hdr.ny = nd[1]; g.hdr.nz = nd[2];
-    const double org[3] = {(double)g.hdr.ox, (double)g.hdr.oy, (double)g.hdr.oz};
-    const double hf = (double)g.hdr.h;  // the cell edge as the device sees it
-    auto range = [&](uint32_t i, int a, int* c0, int* c1) {
-        const float* s = geom4 + 4 * (size_t)i;
-        *c0 = std::min(std::max((int)std::floor(((double)s[a] - radii[i] - inflate - org[a]) / hf), 0), nd[a] - 1);
-        *c1 = std::min(std::max((int)std::floor(((double)s[a] + radii[i] + inflate - org[a]) / hf), 0), nd[a] - 1);
-    };
-    const size_t ncell = (size_t)nd[0] * nd[1] * nd[2];
-    g.cell_start.assign(ncell + 1, 0u);
-    for (int pass = 0; pass < 2; ++pass) {
-        std::vector<uint32_t> fill;
-        if (pass == 1) {
-            for (size_t c = 0, acc = 0; c <= ncell; ++c) {  // counts -> offsets
-                const uint32_t cnt = c < ncell ? g.cell_start[c] : 0u;
-                g.cell_start[c] = (uint32_t)acc;
-                acc += cnt;
+    double r_min = 1e300, r_max = 0.0;
+    for (uint32_t i : small) {
+        r_min = std::min(r_min, (double)radii[i]);
+        r_max = std::max(r_max, (double)radii[i]);
+    }
+    const double h0 = (double)(float)h;  // the cell edge as the device sees it
+    const double diag = std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2]));
+    // tight margin = 5 % of a cell: rounding of the traversal, and the reference's a = 1 shortcut over moderate flights.
+    // loose margin: sized so that a unit-length direction (eps = the rounding floor the device uses, kGridEpsFloor =
+    // 1e-6, plus as much again for |d|^2 - 1) stays covered over 1.5 diagonals of the box, at most one cell.  Small
+    // scenes (the reference's 22 x 22 field) do not need it: there the loose registration is the tight one.
+    const double margin0 = 0.05 * h0;
+    const double far = 1.5 * diag;
+    double margin1 = std::min(std::sqrt(r_min * r_min + 2.0 * 2e-6 * far * far) - r_min, h0);
+    const bool two = margin1 > 1.2 * margin0;
+    if (!two) margin1 = margin0;
+    rtw::GridParams& G = g.hdr;
+    G.h = (float)h0;
+    G.inv_h = 1.0f / G.h;
+    G.safe2_tight = (float)(0.5 * ((r_min + margin0) * (r_min + margin0) - r_min * r_min));  // half of it: slack for rounding
+    G.safe2_loose = (float)(0.5 * ((r_min + margin1) * (r_min + margin1) - r_min * r_min));
+    G.reach = (float)(r_max + margin1);
+    G.r_min = (float)r_min;
+    // the box: [lo, hi] holds every small sphere; pad it by the loose margin + half a cell, so that a ray point within
+    // r + margin of a centre lies inside (the walk then visits a cell the sphere is registered in)
+    const double pad = margin1 + 0.5 * h0;
+    G.pad = (float)(0.999 * pad);
+    G.ox = (float)(lo[0] - pad);
+    G.oy = (float)(lo[1] - pad);
+    G.oz = (float)(lo[2] - pad);
+    const double org[3] = {(double)G.ox, (double)G.oy, (double)G.oz};
+    int ndl[3];
+    for (int a = 0; a < 3; ++a) ndl[a] = std::max(1, (int)std::floor((hi[a] + pad - org[a]) / h0) + 1);
+    G.nx = ndl[0]; G.ny = ndl[1]; G.nz = ndl[2];
+    G.ball_r = (float)(0.5 * h0 * std::sqrt((double)ndl[0] * ndl[0] + (double)ndl[1] * ndl[1] + (double)ndl[2] * ndl[2]) * 1.001);
+    const size_t ncell = (size_t)ndl[0] * ndl[1] * ndl[2];
+    // CSR lists of the spheres whose AABB, inflated by `margin`, touches each cell
+    auto bin = [&](double margin, std::vector<uint32_t>& cell_start, std::vector<uint32_t>& items) {
+        auto range = [&](uint32_t i, int a, int* c0, int* c1) {
+            const float* s = geom4 + 4 * (size_t)i;
+            *c0 = std::min(std::max((int)std::floor(((double)s[a] - radii[i] - margin - org[a]) / h0), 0), ndl[a] - 1);
+            *c1 = std::min(std::max((int)std::floor(((double)s[a] + radii[i] + margin - org[a]) / h0), 0), ndl[a] - 1);
+        };
+        cell_start.assign(ncell + 1, 0u);
+        for (int pass = 0; pass < 2; ++pass) {
+            std::vector<uint32_t> fill;
+            if (pass == 1) {
+                for (size_t c = 0, acc = 0; c <= ncell; ++c) {  // counts -> offsets
+                    const uint32_t cnt = c < ncell ? cell_start[c] : 0u;
+                    cell_start[c] = (uint32_t)acc;
+                    acc += cnt;
+                }
+                items.assign(cell_start[ncell], 0u);
+                fill.assign(cell_start.begin(), cell_start.end() - 1);
             }
-            g.items.assign(g.cell_start[ncell], 0u);
-            fill.assign(g.cell_start.begin(), g.cell_start.end() - 1);
+            for (uint32_t i : small) {  // ascending sphere index, so the items of a cell are ascending too
+                int x0, x1, y0, y1, z0, z1;
+                range(i, 0, &x0, &x1);
+                range(i, 1, &y0, &y1);
+                range(i, 2, &z0, &z1);
+                for (int z = z0; z <= z1; ++z)
+                    for (int y = y0; y <= y1; ++y)
+                        for (int x = x0; x <= x1; ++x) {
+                            const size_t c = (size_t)x + (size_t)ndl[0] * ((size_t)y + (size_t)ndl[1] * z);
+                            if (pass == 0) cell_start[c] += 1u;
+                            else items[fill[c]++] = i;
+                        }
+            }
         }
-        for (uint32_t i : small) {  // ascending sphere index, so the items of a cell are ascending too
-            int x0, x1, y0, y1, z0, z1;
-            range(i, 0, &x0, &x1);
-            range(i, 1, &y0, &y1);
-            range(i, 2, &z0, &z1);
-            for (int z = z0; z <= z1; ++z)
-                for (int y = y0; y <= y1; ++y)
-                    for (int x = x0; x <= x1; ++x) {
-                        const size_t c = (size_t)x + (size_t)nd[0] * ((size_t)y + (size_t)nd[1] * z);
-                        if (pass == 0) g.cell_start[c] += 1u;
-                        else g.items[fill[c]++] = i;
-                    }
-        }
+    };
+    bin(margin0, g.cell_start[0], g.items[0]);
+    if (two) bin(margin1, g.cell_start[1], g.items[1]);
+    // (Coarser levels with a margin of one coarse cell were measured and dropped: a lane walking 100-sphere cells alone
+    // holds its warp for ~30 ordinary segments.  What the loose level cannot cover goes to the cooperative sweep.)
+    if (small.size() > 4096) {
+        // GridCull: every small sphere once, binned by its centre into cells of 16 fine cells; the whole-list sweep of an
+        // unsafe ray visits only the cells its cone of acceptance can reach
+        rtw::GridCull& C = g.hdr.cull;
+        C.h = (float)(16.0 * h0);
+        C.ox = (float)lo[0]; C.oy = (float)lo[1]; C.oz = (float)lo[2];
+        C.r_max = (float)r_max;
+        int nc[3];
+        for (int a = 0; a < 3; ++a) nc[a] = std::max(1, (int)std::floor((hi[a] - (double)(&C.ox)[a]) / (double)C.h) + 1);
+        C.nx = nc[0]; C.ny = nc[1]; C.nz = nc[2];
+        const size_t ncell = (size_t)nc[0] * nc[1] * nc[2];
+        auto cell_of = [&](uint32_t i) {
+            const float* s = geom4 + 4 * (size_t)i;
+            size_t c[3];
+            for (int a = 0; a < 3; ++a)
+                c[a] = (size_t)std::min(std::max((int)std::floor(((double)s[a] - (double)(&C.ox)[a]) / (double)C.h), 0), nc[a] - 1);
+            return c[0] + (size_t)nc[0] * (c[1] + (size_t)nc[1] * c[2]);
+        };
+        g.cull_start.assign(ncell + 1, 0u);
+        for (uint32_t i : small) g.cull_start[cell_of(i) + 1] += 1u;
+        for (size_t c = 0; c < ncell; ++c) g.cull_start[c + 1] += g.cull_start[c];
+        g.cull_items.assign(small.size(), 0u);
+        std::vector<uint32_t> fill(g.cull_start.begin(), g.cull_start.end() - 1);
+        for (uint32_t i : small) g.cull_items[fill[cell_of(i)]++] = i;
     }
 }
 
@@ -570,16 +636,26 @@ int ensure_grid_locked(rtw_ctx* ctx) {
     build_grid(ctx->h_geom.data(), ctx->n_spheres, &hg);
     for (auto& ds : ctx->dev) {
         RTW_CUDA(ctx, cudaSetDevice(ds.device));
-        int grc = grow(ctx, &ds.d_grid_start, &ds.grid_start_cap, hg.cell_start.size());
-        if (!grc) grc = grow(ctx, &ds.d_grid_items, &ds.grid_items_cap, hg.items.size());
-        if (!grc) grc = grow(ctx, &ds.d_grid_big, &ds.grid_big_cap, hg.big.size());
+        int grc = grow(ctx, &ds.d_grid_big, &ds.grid_big_cap, hg.big.size());
+        for (int l = 0; l < 2 && !grc; ++l) {
+            grc = grow(ctx, &ds.d_grid_start[l], &ds.grid_start_cap[l], hg.cell_start[l].size());
+            if (!grc) grc = grow(ctx, &ds.d_grid_items[l], &ds.grid_items_cap[l], hg.items[l].size());
+        }
+        if (!grc) grc = grow(ctx, &ds.d_cull_start, &ds.cull_start_cap, hg.cull_start.size());
+        if (!grc) grc = grow(ctx, &ds.d_cull_items, &ds.cull_items_cap, hg.cull_items.size());
         if (grc) return grc;
-        if (!hg.cell_start.empty())
-            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_grid_start, hg.cell_start.data(), hg.cell_start.size() * 4, cudaMemcpyHostToDevice, ds.stream));
-        if (!hg.items.empty())
-            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_grid_items, hg.items.data(), hg.items.size() * 4, cudaMemcpyHostToDevice, ds.stream));
+        if (!hg.cull_start.empty()) {
+            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_cull_start, hg.cull_start.data(), hg.cull_start.size() * 4, cudaMemcpyHostToDevice, ds.stream));
+            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_cull_items, hg.cull_items.data(), hg.cull_items.size() * 4, cudaMemcpyHostToDevice, ds.stream));
+        }
         if (!hg.big.empty())
             RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_grid_big, hg.big.data(), hg.big.size() * 4, cudaMemcpyHostToDevice, ds.stream));
+        for (int l = 0; l < 2; ++l) {
+            if (hg.cell_start[l].empty()) continue;
+            RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_grid_start[l], hg.cell_start[l].data(), hg.cell_start[l].size() * 4, cudaMemcpyHostToDevice, ds.stream));
+            if (!hg.items[l].empty())
+                RTW_CUDA(ctx, cudaMemcpyAsync(ds.d_grid_items[l], hg.items[l].data(), hg.items[l].size() * 4, cudaMemcpyHostToDevice, ds.stream));
+        }
     }
     for (auto& ds : ctx->dev) {  // the host vectors die with this call
         RTW_CUDA(ctx, cudaSetDevice(ds.device));
@@ -587,6 +663,7 @@ int ensure_grid_locked(rtw_ctx* ctx) {
     }
     ctx->grid = hg.hdr;
     ctx->grid.n_big = (uint32_t)hg.big.size();
+    ctx->grid_two = !hg.cell_start[1].empty();
     ctx->grid_valid = true;
     return RTW_OK;
 }
@@ -709,6 +786,7 @@ int pass_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int max_depth, uint6
             ds.last_resolved = false;
             ds.h_counters[1] = 0;
             ds.h_counters[2] = 0;
+            ds.h_counters[3] = 0;
         }
     }
     if (do_resolve) {
@@ -800,6 +878,7 @@ int pass_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int max_depth, uint6
         total.paths += ds.last.paths;
         total.ray_segments += ds.last.ray_segments;
         total.grid_fallback_rays += ds.last.grid_fallback_rays;
+        total.grid_loose_cells += ds.last.grid_loose_cells;
         total.sphere_tests += ds.last.sphere_tests;
         total.rows_rendered += ds.last.rows_rendered;
         total.kernel_launches += ds.last.kernel_launches;
@@ -1120,7 +1199,8 @@ int rtw_destroy(rtw_ctx* ctx) {
         cudaFree(ds.d_geom_perm[0]); cudaFree(ds.d_geom_perm[1]); cudaFree(ds.d_uv);
         cudaFree(ds.d_geom64); cudaFree(ds.d_mat64); cudaFree(ds.d_kind64);
         cudaFree(ds.d_tile64); cudaFree(ds.d_gather64); cudaFree(ds.d_image64);
-        cudaFree(ds.d_grid_start); cudaFree(ds.d_grid_items); cudaFree(ds.d_grid_big);
+        cudaFree(ds.d_grid_big); cudaFree(ds.d_cull_start); cudaFree(ds.d_cull_items);
+        for (int l = 0; l < 2; ++l) { cudaFree(ds.d_grid_start[l]); cudaFree(ds.d_grid_items[l]); }
         cudaFree(ds.d_accum); cudaFree(ds.d_counters); cudaFree(ds.d_tile);
         cudaFree(ds.d_gather); cudaFree(ds.d_image); cudaFree(ds.d_rgb8); cudaFree(ds.d_scratch); cudaFree(ds.d_wf);
         if (ds.h_counters) cudaFreeHost(ds.h_counters);

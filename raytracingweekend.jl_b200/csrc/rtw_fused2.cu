@@ -481,6 +481,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) fused_trace2_kernel(const 
     int best_k = -1;
     uint32_t seg_count = 0;
     uint32_t fb_count = 0;  // kGrid: rays of this warp resolved by the exact fallback sweep (uniform)
+    uint32_t loose_count = 0;  // kGrid: cells this lane walked with the loose registration
     unsigned long long pool_next = 0, pool_end = 0;  // warp-level ticket pool (uniform)
     bool exhausted = false;
 
@@ -703,10 +704,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) fused_trace2_kernel(const 
         best_t = __int_as_float(0x7f800000);  // typemax(T) = Inf, src/ray_color.jl:19
         best_k = -1;
         if (kGrid) {
-            const bool unsafe = closest_hit_grid(P.grid, P.geom, o, d, alive, best_t, best_k);
+            const bool unsafe = closest_hit_grid(P.grid, P.geom, o, d, alive, best_t, best_k, loose_count);
             // rays the grid cannot answer exactly (non-unit direction after a glass reflection, very long flights):
             // warp-cooperative sweep of the whole list, for every list size -- the mode is exact by construction
-            fb_count += grid_fallback_sweep(P.geom, n, o, d, unsafe, best_t, best_k);
+            fb_count += grid_fallback_sweep(P.grid.cull, P.geom, n, o, d, unsafe, best_t, best_k);
         } else {
             const uint32_t h = threadIdx.x & (kCoop - 1);
             f3 so[kCoop], sd[kCoop];
@@ -760,6 +761,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) fused_trace2_kernel(const 
     for (int off = 16; off > 0; off >>= 1) seg_count += __shfl_xor_sync(kFullMask, seg_count, off);
     if (lane == 0 && seg_count) atomicAdd(P.counters + 1, (unsigned long long)seg_count);
     if (kGrid && lane == 0 && fb_count) atomicAdd(P.counters + 2, (unsigned long long)fb_count);
+    if (kGrid) {
+        for (int off = 16; off > 0; off >>= 1) loose_count += __shfl_xor_sync(kFullMask, loose_count, off);
+        if (lane == 0 && loose_count) atomicAdd(P.counters + 3, (unsigned long long)loose_count);
+    }
 }
 
 // u_tab[col] = T((col+1)/W), v_tab[i0] = T((H-1-i0)/H) (src/render.jl:26-27): the quotient is formed in Float64 and
@@ -827,7 +832,8 @@ cudaError_t launch_uv_tables(int W, int H, float* u_tab, float* v_tab, cudaStrea
 
 cudaError_t launch_fused_trace2_grid(const TraceParams& p, int num_sms, int blocks_per_sm_override, cudaStream_t stream,
                                      LaunchInfo* info) {
-    auto kern = fused_trace2_kernel<false, 2, false, true>;
+    // 64 registers, 4 CTAs per SM: the traversal is latency-bound and wants the warps
+    auto kern = fused_trace2_kernel<false, 2, false, true, 4>;
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTraceBlock, 0);
     if (e != cudaSuccess) return e;

@@ -18,16 +18,33 @@ struct MagicDiv {
     uint32_t m, sh1, sh2;
 };
 
-// RTW_MODE_GRID: uniform grid over the small spheres + list of big ones (rtw_grid.cuh); nx == 0: no grid
-struct GridParams {
-    float ox, oy, oz;  // minimum corner
-    float h, inv_h;    // cell edge
-    float safe2;       // (r_min + inflate)^2 - r_min^2: the growth of r^2 the registration margin covers (rtw_grid.cuh)
-    int nx, ny, nz;
+// RTW_MODE_GRID: a uniform grid over the small spheres + a list of big ones (rtw_grid.cuh); nx == 0: no grid.
+// The cells carry TWO registrations of the small spheres (CSR lists of the spheres whose AABB, inflated by a margin,
+// touches the cell): a tight one (5 % of a cell) for the near part of a flight and a loose one (up to one cell) for
+// the far part, where the reference's arithmetic lets spheres grow (rtw_grid.cuh).  On small scenes both are the same.
+struct GridCull {  // by-centre binning into coarse cells: lets the exact sweep of an unsafe ray skip what it cannot reach
+    float ox, oy, oz, h;
+    int nx, ny, nz;              // nx == 0: no culling, the sweep visits the whole list
+    float r_max;                 // largest small radius
     const uint32_t* cell_start;  // nx*ny*nz + 1 offsets into items
-    const uint32_t* items;       // sphere indices per cell, ascending
-    const uint32_t* big;         // spheres every ray tests
+    const uint32_t* items;       // every small sphere exactly once, ascending within a cell
+};
+struct GridParams {
+    float ox, oy, oz;  // minimum corner: the extent of the small spheres padded by `pad`
+    float h, inv_h;    // cell edge
+    int nx, ny, nz;
+    float safe2_tight, safe2_loose;  // ((r_min + margin)^2 - r_min^2) / 2: the growth of r^2 each registration covers
+    float reach;       // largest small radius + loose margin: how far from its centre a registered sphere can matter
+    float pad;         // how far the box extends beyond the real spheres (loose margin + half a cell)
+    float r_min;       // smallest small radius (the sphere whose apparent size grows fastest)
+    float ball_r;      // half the diagonal of the box
+    const uint32_t* cell_start_tight;  // nx*ny*nz + 1 offsets into items_tight
+    const uint32_t* items_tight;       // sphere indices per cell, ascending
+    const uint32_t* cell_start_loose;
+    const uint32_t* items_loose;
+    const uint32_t* big;  // spheres every ray tests
     uint32_t n_big;
+    GridCull cull;
 };
 
 struct TraceParams {

@@ -810,3 +810,53 @@ def test_cfg5_headline_width_row_matches_the_oracle(rtw, oracle, renderer, mode)
     ref, _, ost = oracle.render(*scene, cam.as_array(), W, spp, max_depth=depth, seed=1, row_start=row, row_stride=H)
     assert st["ray_segments"] == ost["ray_segments"]
     _compare(tile.cpu().numpy()[0], np.ascontiguousarray(ref[row]))
+
+
+def _large_soup(rtw, rng, n, trial):
+    """A wide, flat field of small spheres (the shape of BASELINE configs[4]) made adversarial for a grid: glass-heavy
+    (un-normalised reflections, src/material.jl:48), radii over a decade, a few hollow ones, rays that graze the field
+    for hundreds of units, optionally a huge ground sphere."""
+    ext = 0.5 * np.sqrt(n)
+    centers = np.stack([rng.uniform(-ext, ext, n), rng.uniform(0.05, 0.6, n), rng.uniform(-ext, ext, n)], axis=1)
+    radii = (10.0 ** rng.uniform(-1.2, -0.5, size=n))
+    radii[rng.random(n) < 0.03] *= -1.0
+    geom = np.concatenate([centers, radii[:, None]], axis=1).astype(np.float32)
+    if trial % 2 == 0:
+        geom[0] = [0, -1000, 0, 1000]
+    kind = rng.choice([0, 1, 2], size=n, p=[0.4, 0.2, 0.4]).astype(np.uint32)
+    mat = rng.uniform(0.3, 1.0, size=(n, 4)).astype(np.float32)
+    mat[kind == 1, 3] = rng.uniform(0, 1.0, size=int((kind == 1).sum()))
+    mat[kind == 2] = [1.0, 1.0, 1.0, 1.5]
+    mat[kind == 0, 3] = 0.0
+    if trial % 3 == 0:   # grazing view along the field from one corner: flights of several hundred units
+        cam = rtw.default_camera([-ext, 0.4, -ext], [ext, 0.2, ext], [0, 1, 0], 30, 16 / 9, 0.0, 1.0)
+    elif trial % 3 == 1:  # from inside the field
+        cam = rtw.default_camera([0.3, 0.35, 0.1], [ext, 0.3, 0.2 * ext], [0, 1, 0], 70, 16 / 9, 0.05, 2.0)
+    else:
+        cam = rtw.default_camera([0.6 * ext, 3.0, 0.6 * ext], [0, 0, 0], [0, 1, 0], 40, 16 / 9, 0.0, 1.0)
+    return (geom, mat, kind), cam
+
+
+@pytest.mark.parametrize("n", [5000, 20000, 100000])
+def test_grid_mode_large_soups_are_exact(rtw, oracle, renderer, n):
+    # RTW_MODE_GRID is exact for EVERY list size: lists beyond one shared-memory tile, up to the size of BASELINE
+    # configs[4], with the rays a grid handles worst.  All three tiers must fire somewhere in the set (tight walk, loose
+    # registration, whole-list sweep) and every image must equal the oracle's, segment for segment.
+    rng = np.random.default_rng(n)
+    renderer.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_GRID)
+    loose = sweep = 0
+    try:
+        for trial in range(3):
+            scene, cam = _large_soup(rtw, rng, n, trial)
+            img = renderer.render(cam, 64, 4, max_depth=12, seed=trial, scene=scene)
+            st = dict(renderer.last_stats)
+            ref, _, ost = oracle.render(*scene, cam.as_array(), 64, 4, max_depth=12, seed=trial)
+            assert st["ray_segments"] == ost["ray_segments"], (n, trial)
+            _compare(img, ref)
+            loose += st["grid_loose_cells"]
+            sweep += st["grid_fallback_rays"]
+    finally:
+        renderer.set_option(rtw.RTW_OPT_MODE, rtw.RTW_MODE_FUSED)
+    assert sweep > 0, "no ray reached the whole-list sweep: the set does not exercise tier 3"
+    if n >= 20000:
+        assert loose > 0, "no ray used the loose registration: the set does not exercise tier 2"

@@ -58,6 +58,8 @@ __global__ void __launch_bounds__(kTraceBlock, 3) trace_f64_kernel(const __grid_
     extern __shared__ __align__(16) unsigned char smem_raw64[];
     double4* s_geom = reinterpret_cast<double4*>(smem_raw64);
     const uint32_t n = P.n_spheres;
+    // kShared: one 32-test candidate mask per chunk and lane, behind the list (word c of a lane at (c * block + tid))
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_geom + (kShared ? n : 0u)) + threadIdx.x;
     if (kShared) {
         for (uint32_t i = threadIdx.x; i < n; i += kTraceBlock) s_geom[i] = P.geom[i];
         __syncthreads();
@@ -164,9 +166,94 @@ __global__ void __launch_bounds__(kTraceBlock, 3) trace_f64_kernel(const __grid_
             best_t = root;
             best_k = (int)k;
         };
+        if constexpr (kShared) {
+            // ---- lists <= 1024 spheres, in shared memory.  Two lanes cooperate: a broadcast LDS.128 delivers 512 B to the
+            // warp and the shared-memory pipe moves 128 B/clk/SM, so with two loads per test (a double4) the sweep of four
+            // sub-partitions would need 32 LSU cycles per 22 FP64 cycles -- the first version of this kernel ran at exactly
+            // that ratio (72 % of the FP64 pipe).  Lane h of a pair tests BOTH rays of the pair against the spheres
+            // 64c + 2j + h (j = 0..31) of super-chunk c: one load per test.  Per test still 3 DADD + 2 DMUL + 6 DFMA; the
+            // sign bit of each discriminant goes into a 32-test mask by one funnel shift, masks go to shared memory, and
+            // after the sweep every lane resolves the candidates of ITS OWN ray (its slot-0 words and its partner's slot-1
+            // words) in one loop -- closest hit in the order-independent form: min over the spheres of the first root
+            // >= tmin, ties to the larger list index (the sequential sweep lets the later sphere win, src/hit.jl:24-26,44-46).
+            const uint32_t h = threadIdx.x & 1u;
+            const d3 o1 = mkd(__shfl_xor_sync(kFullMask, o.x, 1), __shfl_xor_sync(kFullMask, o.y, 1), __shfl_xor_sync(kFullMask, o.z, 1));
+            const d3 d1 = mkd(__shfl_xor_sync(kFullMask, d.x, 1), __shfl_xor_sync(kFullMask, d.y, 1), __shfl_xor_sync(kFullMask, d.z, 1));
+            auto disc_hi = [&](const double4 s, const d3 ro, const d3 rd) {
+                const d3 oc = mkd(ro.x - s.x, ro.y - s.y, ro.z - s.z);
+                const double hb = dotd(oc, rd);
+                const double cq = fma(-s.w, s.w, dotd(oc, oc));
+                return (uint32_t)__double2hiint(fma(hb, hb, -cq));
+            };
+            uint32_t summary = 0u;  // bit 2c + q: mask word (super-chunk c, slot q) holds a candidate
+            const uint32_t nfull = n >> 6;
+            const double4* lp = list + h;
+            uint32_t* mp = s_mask;
+            for (uint32_t c = 0; c < nfull; ++c) {
+                uint32_t m0 = 0u, m1 = 0u;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const double4 s = lp[2 * j];
+                    m0 = __funnelshift_l(disc_hi(s, o, d), m0, 1);  // test j ends at bit 31 - j; set = miss
+                    m1 = __funnelshift_l(disc_hi(s, o1, d1), m1, 1);
+                }
+                mp[0] = m0;
+                mp[kTraceBlock] = m1;
+                summary |= ((m0 != 0xffffffffu ? 1u : 0u) | (m1 != 0xffffffffu ? 2u : 0u)) << (2u * c);
+                lp += 64;
+                mp += 2 * kTraceBlock;
+            }
+            const uint32_t rem = n - (nfull << 6);  // 0 .. 63 spheres in the ragged last super-chunk
+            if (rem != 0u) {
+                uint32_t m0 = 0u, m1 = 0u;
+                const uint32_t run = (rem + 1u) >> 1;  // tests every lane runs (uniform); lane h owns (rem - h + 1) / 2 of them
+                for (uint32_t j = 0; j < run; ++j) {
+                    const uint32_t idx = 2u * j + h;
+                    const double4 s = lp[idx < rem ? 2u * j : 0u];
+                    m0 = __funnelshift_l(disc_hi(s, o, d), m0, 1);
+                    m1 = __funnelshift_l(disc_hi(s, o1, d1), m1, 1);
+                }
+                const uint32_t mine = (rem + 1u - h) >> 1;
+                const uint32_t sh = 32u - run;                                 // left-align the tests that were executed
+                const uint32_t fill = mine >= 32u ? 0u : (0xffffffffu >> mine);  // everything below this lane's real tests = miss
+                m0 = (m0 << sh) | fill;
+                m1 = (m1 << sh) | fill;
+                mp[0] = m0;
+                mp[kTraceBlock] = m1;
+                summary |= ((m0 != 0xffffffffu ? 1u : 0u) | (m1 != 0xffffffffu ? 2u : 0u)) << (2u * nfull);
+            }
+            __syncwarp();  // the partner's mask words are visible
+            uint32_t sum = (summary & 0x55555555u) | (__shfl_xor_sync(kFullMask, summary, 1) & 0xaaaaaaaau);
+            if (!alive) sum = 0u;
+            const uint32_t* mbase = s_mask - threadIdx.x;
+            while (sum) {
+                const uint32_t w = (uint32_t)__ffs((int)sum) - 1u;  // = 2c + q: word of lane tid ^ q, which tests spheres 64c + 2j + (h ^ q)
+                sum &= sum - 1u;
+                const uint32_t q = w & 1u;
+                uint32_t cand = ~mbase[w * kTraceBlock + (threadIdx.x ^ q)];
+                const uint32_t kb = (w >> 1) * 64u + (h ^ q);
+                while (cand) {
+                    const uint32_t j = (uint32_t)__clz((int)cand);
+                    cand &= ~(0x80000000u >> j);
+                    const uint32_t k = kb + 2u * j;
+                    const double4 s = list[k];
+                    const d3 oc = mkd(o.x - s.x, o.y - s.y, o.z - s.z);
+                    const double hb = dotd(oc, d);
+                    const double cq = fma(-s.w, s.w, dotd(oc, oc));
+                    const double sq = sqrt(fma(hb, hb, -cq));
+                    const double r1 = -hb - sq, r2 = -hb + sq;  // src/hit.jl:23, 25
+                    const double t = r1 < tmin ? r2 : r1;       // the first root >= tmin, if any
+                    if (t >= tmin && (t < best_t || (t == best_t && (int)k > best_k))) {
+                        best_t = t;
+                        best_k = (int)k;
+                    }
+                }
+            }
+            __syncwarp();  // all reads of the partner's words are done before the next sweep overwrites them
+        } else {
         uint32_t k = 0;
-        // whole chunks of 32 spheres: branch-free discriminants (3 DADD + 2 DMUL + 6 DFMA per test), the sign bit of
-        // each goes into a 32-test mask by one funnel shift; the lane then resolves only its own candidates
+        // streamed lists (> 1024 spheres, read through L1/L2): whole chunks of 32 spheres, branch-free discriminants,
+        // candidates resolved chunk by chunk in list order
         for (; k + 32u <= n; k += 32u) {
             uint32_t m = 0u;
 #pragma unroll
@@ -187,6 +274,7 @@ __global__ void __launch_bounds__(kTraceBlock, 3) trace_f64_kernel(const __grid_
         }
         if (alive)
             for (; k < n; ++k) resolve(k);  // ragged tail
+        }
         // ---- shade / scatter / accumulate
         if (alive) {
             seg_count += 1;
@@ -285,10 +373,13 @@ __global__ void __launch_bounds__(256) assemble_f64_kernel(const double* __restr
 
 cudaError_t launch_trace_f64(const TraceParams64& p, int num_sms, cudaStream_t stream, LaunchInfo* info) {
     const bool shared = p.n_spheres <= kTileSpheres;
-    const int smem = shared ? (int)(p.n_spheres * sizeof(double4)) : 0;
+    // shared: the list + (per lane) two mask words per super-chunk of 64 spheres
+    const int smem = shared ? (int)(p.n_spheres * sizeof(double4) + 2u * (p.n_spheres / 64u + 1u) * kTraceBlock * 4u) : 0;
     cudaError_t e = cudaSuccess;
     int per_sm = 0;
     if (shared) {
+        e = cudaFuncSetAttribute(trace_f64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_f64_kernel<true>, kTraceBlock, smem);
     } else {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_f64_kernel<false>, kTraceBlock, 0);

@@ -594,20 +594,21 @@ def run_extras(args, R, r, scene, cam, stream, timed_steps, one_step_resident, n
                           "workload": f"scene_random_spheres(Float64), t_cam1, {W}x{R.image_height(W)}, {spp64} spp, depth {depth}"}
     except Exception as e:
         out["float64"] = {"error": str(e)}
-    try:  # the reference's own small renders through the host-buffer call (wall clock, best of 50)
+    try:  # the reference's own small renders through the host-buffer call rtw_render_scene (wall clock incl. the Python
+        # binding, best of 50); they take the single-launch latency path (csrc/rtw_small.cu)
         lat = {}
         cases = [("scene_2_spheres_96x54x1", R.flatten_scene(R.scene_2_spheres()), R.t_default_cam(), 96, 1),
                  ("scene_2_spheres_96x54x16", R.flatten_scene(R.scene_2_spheres()), R.t_default_cam(), 96, 16),
                  ("random_spheres_96x54x1", scene, cam, 96, 1)]
         for name, sc, cm, w, s in cases:
-            r.set_scene(sc)
             buf = np.empty((w, R.image_height(w), 3), dtype=np.float32)
             best = 1e9
-            for _ in range(50):
+            for _ in range(50):  # one rtw_render_scene per call: scene arrays, camera and image are host buffers
                 t0 = time.perf_counter()
-                r.render(cm, w, s, out=buf)
+                r.render(cm, w, s, scene=sc, out=buf)
                 best = min(best, time.perf_counter() - t0)
             lat[name] = best * 1e6
+            lat[name + "_kernel_launches"] = r.last_stats["kernel_launches"]
         lat["reference_us"] = {"scene_2_spheres_96x54x1": 101, "scene_2_spheres_96x54x16": 951, "random_spheres_96x54x1": 2040,
                                "source": "src/proto/proto.jl:87-89, :64-66, :142-144 (Ryzen 3700X, 16 threads, Float64)"}
         out["latency_us"] = lat

@@ -106,6 +106,11 @@ typedef struct rtw_ctx rtw_ctx;
 
 #define RTW_OPT_GATHER 10         /* RTW_GATHER_*: how a multi-device context collects the row tiles on device 0 */
 
+#define RTW_OPT_SMALL_RENDER 11    /* 1 (default): a small render() on a one-device context (<= 2^17 paths, <= 1024 spheres,
+                                     default kernel options) runs as ONE kernel launch with the image written to mapped
+                                     host memory -- the latency path for the reference's own 96x54 smoke/benchmark sizes;
+                                     0: always the persistent kernel.  Same image bits either way. */
+
 #define RTW_GATHER_PEER 0         /* cudaMemcpyPeerAsync on each producer's stream (default; measured fastest)  */
 #define RTW_GATHER_NCCL 1         /* one grouped ncclSend/ncclRecv (single-process ncclCommInitAll); libnccl.so.2 is
                                      bound with dlopen on first use -- RTW_E_UNSUPPORTED when it is not installed   */

@@ -9,7 +9,7 @@ package's API surface (src/RayTracingWeekend.jl:10-31) used to drive it.
 
 The directory name contains a dot, so import it through the repo-root alias module `rtw_b200`.
 """
-from ._lib import (RTW_GATHER_NCCL, RTW_GATHER_PEER, RTW_OPT_GATHER)
+from ._lib import (RTW_GATHER_NCCL, RTW_GATHER_PEER, RTW_OPT_GATHER, RTW_OPT_SMALL_RENDER)
 from ._lib import (EXPORTED_SYMBOLS, LIB_PATH, RTW_MODE_CTA_WAVEFRONT, RTW_MODE_FUSED, RTW_MODE_GRID, RTW_MODE_WAVEFRONT, RTW_OPT_BLOCKS_PER_SM,
                    RTW_OPT_COLLECT_TIMING, RTW_OPT_COOP, RTW_OPT_MODE, RTW_OPT_RAYS_PER_LANE, RTW_OPT_STRIP, RTW_OPT_SWEEP,
                    RTW_OPT_TAIL, RTW_OPT_WALK, RTW_WALK_DEFAULT, RTW_WALK_OWN_RAY, RTW_WALK_SLOTS, RTW_TAIL_DEFAULT, RTW_TAIL_SPLIT, RTW_TAIL_UNIFIED, RtwError, rtw_camera, rtw_stats)

@@ -67,6 +67,7 @@ RTW_OPT_TAIL = 8
 
 RTW_OPT_WALK = 9
 RTW_OPT_GATHER = 10
+RTW_OPT_SMALL_RENDER = 11
 RTW_GATHER_PEER = 0
 RTW_GATHER_NCCL = 1
 RTW_WALK_DEFAULT = 0

@@ -19,7 +19,21 @@ DEFAULT_MAX_DEPTH = 16  # ray_color's default depth, src/ray_color.jl:14
 DEFAULT_SEED = 1        # reseed!() semantics: the same image on every call, src/render.jl:21
 
 
+_cam_cache = {}
+
+
 def _camera_struct(cam: Camera) -> rtw_camera:
+    hit = _cam_cache.get(id(cam))
+    if hit is not None and hit[0] is cam:  # Camera is frozen: the struct of the same object never changes
+        return hit[1]
+    c = _camera_struct_uncached(cam)
+    if len(_cam_cache) > 64:
+        _cam_cache.clear()
+    _cam_cache[id(cam)] = (cam, c)
+    return c
+
+
+def _camera_struct_uncached(cam: Camera) -> rtw_camera:
     if cam.elem_type != F32:
         raise RtwError(_lib.RTW_E_UNSUPPORTED, "this entry point takes a Camera{Float32} (render() also serves Camera{Float64})")
     c = rtw_camera()

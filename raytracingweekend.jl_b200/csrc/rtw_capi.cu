@@ -69,6 +69,11 @@ struct DeviceState {
     float* d_scratch = nullptr;
     unsigned char* d_wf = nullptr;  // RTW_MODE_WAVEFRONT path pool
     size_t wf_cap = 0;              // bytes
+    // latency path (rtw_small.cu): image and totals in mapped pinned host memory, device counters kept zero between calls
+    float* h_small_img = nullptr;
+    size_t small_img_cap = 0;  // floats
+    unsigned long long* h_small_tot = nullptr;
+    bool counters_clean = false;
     // last resident render
     rtw_stats last = {};
     cudaStream_t last_stream = nullptr;
@@ -102,6 +107,9 @@ struct rtw_ctx {
     bool grid_two = false;      // the loose registration has lists of its own (large scenes)
     bool grid_valid = false;    // the grid of the current scene has been built and uploaded (lazily: RTW_MODE_GRID only)
     std::vector<float> h_geom;  // host copy of geom4, kept for the lazy grid build
+    std::vector<float> h_mat;   // host copies of mat4 / kind: rtw_set_scene with an unchanged scene is a no-op
+    std::vector<uint32_t> h_kind;
+    int small_render = 1;       // RTW_OPT_SMALL_RENDER: small renders take the single-launch latency path
     float max_albedo = 0.f;     // largest albedo component of the scene (fixed-point head-room check)
     double max_albedo64 = 0.0;  // the same for the Float64 scene
     int mode = RTW_MODE_FUSED;
@@ -331,6 +339,7 @@ int enqueue_trace(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, i
     if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[0], stream));
     if (ps.reset) RTW_CUDA(ctx, cudaMemsetAsync(ds.d_accum, 0, npix * 4 * sizeof(unsigned long long), stream));
     RTW_CUDA(ctx, cudaMemsetAsync(ds.d_counters, 0, kCounters * sizeof(unsigned long long), stream));
+    ds.counters_clean = false;
 
     const int fx_bits = fx_bits_for(ps.s_total);
     int launches = 0;
@@ -682,6 +691,12 @@ int set_scene_locked(rtw_ctx* ctx, const float* geom4, const float* mat4, const 
                 max_albedo = std::max(max_albedo, a);
             }
     }
+    // The same scene again (the drop-in render(scene, cam, ...) passes it with every call): nothing to upload.
+    if (ctx->have_scene && n == ctx->n_spheres && ctx->h_geom.size() == 4 * (size_t)n &&
+        (n == 0 || (std::memcmp(ctx->h_geom.data(), geom4, 16 * (size_t)n) == 0 &&
+                    std::memcmp(ctx->h_mat.data(), mat4, 16 * (size_t)n) == 0 &&
+                    std::memcmp(ctx->h_kind.data(), kind, 4 * (size_t)n) == 0)))
+        return RTW_OK;
     // From here on the previous scene is gone: a failure below must not leave a context that claims to hold one
     // (device arrays freed / half uploaded).  Re-validated only after every device has synchronised.
     ctx->have_scene = false;
@@ -690,6 +705,8 @@ int set_scene_locked(rtw_ctx* ctx, const float* geom4, const float* mat4, const 
     ctx->grid = rtw::GridParams{};
     ctx->prog = ProgressiveState{};  // a progressive image belongs to the scene it was traced on
     ctx->h_geom.assign(geom4, geom4 + 4 * (size_t)n);  // for the lazy grid build (RTW_MODE_GRID only)
+    ctx->h_mat.assign(mat4, mat4 + 4 * (size_t)n);
+    ctx->h_kind.assign(kind, kind + (size_t)n);
     ctx->max_albedo = max_albedo;
     // pair layout of the geometry for the packed sweep: spheres (2p, 2p+1) -> {xa,xb,ya,yb}{za,zb,ra,rb}
     std::vector<float> pairs((size_t)((n + 1u) / 2u) * 8u, 0.0f);
@@ -899,12 +916,93 @@ int pass_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int max_depth, uint6
     return RTW_OK;
 }
 
+// The latency path: a small render() on one device in ONE kernel launch (rtw_small.cu) -- no memsets, no u/v tables, no
+// resolve kernel, no enqueued copies; the image lands in mapped pinned memory and is memcpy'd to the caller's buffer.
+bool small_render_eligible(const rtw_ctx* ctx, int W, int spp, int max_depth) {
+    if (!ctx->small_render || ctx->dev.size() != 1 || ctx->mode != RTW_MODE_FUSED) return false;
+    if (ctx->rays_per_lane || ctx->sweep || ctx->coop || ctx->tail || ctx->walk || ctx->blocks_per_sm) return false;  // a variant was asked for
+    if (ctx->n_spheres > rtw::kTileSpheres || max_depth < 1) return false;
+    const long long H = rtw_image_height(W);
+    const long long paths = (long long)W * H * spp;
+    return H > 0 && paths <= (1 << 17) && paths * (long long)std::max<uint32_t>(ctx->n_spheres, 8u) <= (1ll << 22);
+}
+
+int small_render_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int spp, int max_depth, uint64_t seed, float* out_rgb,
+                        rtw_stats* stats) {
+    DeviceState& ds = ctx->dev[0];
+    const int H = rtw_image_height(W);
+    const size_t img_floats = (size_t)W * (size_t)H * 3;
+    const bool timing = ctx->collect_timing != 0;
+    RTW_CUDA(ctx, cudaSetDevice(ds.device));
+    if (img_floats > ds.small_img_cap || !ds.h_small_img) {
+        if (ds.h_small_img) RTW_CUDA(ctx, cudaFreeHost(ds.h_small_img));
+        ds.h_small_img = nullptr;
+        ds.small_img_cap = 0;
+        RTW_CUDA(ctx, cudaHostAlloc((void**)&ds.h_small_img, std::max<size_t>(img_floats, 1 << 16) * sizeof(float), cudaHostAllocMapped));
+        ds.small_img_cap = std::max<size_t>(img_floats, 1 << 16);
+    }
+    if (!ds.h_small_tot) RTW_CUDA(ctx, cudaHostAlloc((void**)&ds.h_small_tot, 64, cudaHostAllocMapped));
+    if (!ds.counters_clean) {
+        RTW_CUDA(ctx, cudaMemsetAsync(ds.d_counters, 0, kCounters * sizeof(unsigned long long), ds.stream));
+        ds.counters_clean = true;  // the kernel leaves them zero
+    }
+    ds.h_small_tot[0] = 0;
+    rtw::TraceParams p{};
+    p.cam = to_dev_camera(cam);
+    p.geom = ds.d_geom;
+    p.mat = ds.d_mat;
+    p.kind = ds.d_kind;
+    p.n_spheres = ctx->n_spheres;
+    p.W = W; p.H = H; p.spp = spp; p.max_depth = max_depth;
+    p.sample_first = 0;
+    p.key0 = (uint32_t)seed; p.key1 = (uint32_t)(seed >> 32);
+    p.row_start = 0; p.row_stride = 1; p.n_rows = H;
+    p.n_paths = (unsigned long long)W * H * spp;
+    const int fx_bits = fx_bits_for(spp);
+    p.fx_scale = std::ldexp(1.0, fx_bits);
+    p.counters = ds.d_counters;
+    float* d_img = nullptr;
+    unsigned long long* d_tot = nullptr;
+    RTW_CUDA(ctx, cudaHostGetDevicePointer((void**)&d_img, ds.h_small_img, 0));
+    RTW_CUDA(ctx, cudaHostGetDevicePointer((void**)&d_tot, ds.h_small_tot, 0));
+    rtw::LaunchInfo li{};
+    if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[0], ds.stream));
+    RTW_CUDA(ctx, rtw::launch_small_render(p, std::ldexp(1.0, -fx_bits), d_img, d_tot, ds.stream, &li));
+    if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[1], ds.stream));
+    RTW_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+    std::memcpy(out_rgb, ds.h_small_img, img_floats * sizeof(float));
+    rtw_stats st = {};
+    st.n_spheres = ctx->n_spheres;
+    st.image_width = W;
+    st.image_height = H;
+    st.rows_rendered = H;
+    st.paths = p.n_paths;
+    st.ray_segments = ds.h_small_tot[0];
+    st.sphere_tests = st.ray_segments * (uint64_t)ctx->n_spheres;
+    st.kernel_launches = 1;
+    st.n_devices = 1;
+    if (timing) {
+        float ms = 0.f;
+        RTW_CUDA(ctx, cudaEventElapsedTime(&ms, ds.ev[0], ds.ev[1]));
+        st.ms_trace = st.ms_total = ms;
+    }
+    ds.last = st;
+    ds.last_valid = true;
+    ds.last_stream = ds.stream;
+    ds.last_resolved = true;
+    ds.h_counters[1] = st.ray_segments;  // rtw_last_stats re-reads the pinned mirror
+    ds.h_counters[2] = ds.h_counters[3] = 0;
+    if (stats) *stats = st;
+    return RTW_OK;
+}
+
 int render_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int spp, int max_depth, uint64_t seed, float* out_rgb,
                   rtw_stats* stats, bool scene_uploaded_in_call) {
     int rc = check_render_args(ctx, cam, W, spp, max_depth);
     if (rc) return rc;
     if (!out_rgb) return fail(ctx, RTW_E_INVALID_ARG, "out_rgb is NULL");
     ctx->prog = ProgressiveState{};  // a plain render() owns the accumulators: any progressive image is gone
+    if (small_render_eligible(ctx, W, spp, max_depth)) return small_render_locked(ctx, cam, W, spp, max_depth, seed, out_rgb, stats);
     return pass_locked(ctx, cam, W, max_depth, seed, PassSpec{0, spp, spp, true}, true, true, spp, out_rgb, nullptr, stats,
                        scene_uploaded_in_call);
 }
@@ -1003,6 +1101,7 @@ int render_f64_locked(rtw_ctx* ctx, const rtw_camera_f64* cam, int W, int spp, i
         if (timing) RTW_CUDA(ctx, cudaEventRecord(ds.ev[0], ds.stream));
         RTW_CUDA(ctx, cudaMemsetAsync(ds.d_accum, 0, npix * 4 * sizeof(unsigned long long), ds.stream));
         RTW_CUDA(ctx, cudaMemsetAsync(ds.d_counters, 0, kCounters * sizeof(unsigned long long), ds.stream));
+        ds.counters_clean = false;
         int launches = 0;
         if (max_depth > 0) {
             rtw::TraceParams64 p;
@@ -1204,6 +1303,8 @@ int rtw_destroy(rtw_ctx* ctx) {
         cudaFree(ds.d_accum); cudaFree(ds.d_counters); cudaFree(ds.d_tile);
         cudaFree(ds.d_gather); cudaFree(ds.d_image); cudaFree(ds.d_rgb8); cudaFree(ds.d_scratch); cudaFree(ds.d_wf);
         if (ds.h_counters) cudaFreeHost(ds.h_counters);
+        if (ds.h_small_img) cudaFreeHost(ds.h_small_img);
+        if (ds.h_small_tot) cudaFreeHost(ds.h_small_tot);
         for (auto& e : ds.ev) if (e) cudaEventDestroy(e);
         if (ds.ev_tile) cudaEventDestroy(ds.ev_tile);
         if (ds.stream) cudaStreamDestroy(ds.stream);
@@ -1258,6 +1359,9 @@ int rtw_set_option(rtw_ctx* ctx, int option, int64_t value) {
             return RTW_OK;
         case RTW_OPT_COLLECT_TIMING:
             ctx->collect_timing = value != 0;
+            return RTW_OK;
+        case RTW_OPT_SMALL_RENDER:
+            ctx->small_render = value != 0;
             return RTW_OK;
         case RTW_OPT_GATHER:
             if (value != RTW_GATHER_PEER && value != RTW_GATHER_NCCL) return fail(ctx, RTW_E_INVALID_ARG, "unknown gather");

@@ -146,6 +146,9 @@ cudaError_t launch_resolve(const unsigned long long* accum, int W, int H, int n_
 cudaError_t launch_assemble(const float* tiles, int n_tiles, int W, int H, float* out, cudaStream_t stream);
 // Julia column-major Float32 image -> row-major 8-bit RGB, clamp01nan + N0f8 rounding (rtw_image.cu)
 cudaError_t launch_quantize_rgb8(const float* img, int W, int H, unsigned char* out, cudaStream_t stream);
+// latency path (rtw_small.cu): a whole small render in one launch; both device counters must be zero on entry
+cudaError_t launch_small_render(const TraceParams& p, double inv_scale, float* out_img, unsigned long long* host_totals,
+                                cudaStream_t stream, LaunchInfo* info);
 // Float64 path (rtw_f64.cu)
 cudaError_t launch_trace_f64(const TraceParams64& p, int num_sms, cudaStream_t stream, LaunchInfo* info);
 cudaError_t launch_resolve_f64(const unsigned long long* accum, int W, int H, int n_rows, int row_start, int row_stride,

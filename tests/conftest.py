@@ -41,6 +41,9 @@ def rtw():
 def renderer(rtw):
     """A GPU renderer; GPU tests FAIL (not skip) when the CUDA library cannot run -- no silent fallback."""
     r = rtw.Renderer([0])
+    # the parity tests are about the persistent kernel: keep small images on it (tests/test_gpu_small_render.py covers
+    # the single-launch latency path that small renders take by default)
+    r.set_option(rtw.RTW_OPT_SMALL_RENDER, 0)
     yield r
     r.close()
 

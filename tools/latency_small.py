@@ -16,11 +16,10 @@ cases += [("random_spheres 200x112x32 (src/proto/proto.jl:195-200; reference: 29
 with R.Renderer([0]) as r:
     for name, scene, cam, W, spp in cases:
         flat = R.flatten_scene(scene)
-        r.set_scene(flat)
         best_wall, best = 1e9, None
         for _ in range(30):
             t0 = time.perf_counter()
-            r.render(cam, W, spp)
+            r.render(cam, W, spp, scene=flat)  # rtw_render_scene: what the Julia render(scene, cam, W, spp) binds to
             wall = time.perf_counter() - t0
             if wall < best_wall:
                 best_wall, best = wall, dict(r.last_stats)

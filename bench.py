@@ -551,8 +551,9 @@ def run_extras(args, R, r, scene, cam, stream, timed_steps, one_step_resident, n
     finally:
         r.set_option(R.RTW_OPT_MODE, R.RTW_MODE_FUSED)
     try:  # BASELINE configs[4]: ~100k spheres, 1920x1080, 256 spp (full), grid mode
+        R.reseed()
         t0 = time.perf_counter()
-        big = r.generate_random_spheres(158) if hasattr(r, "generate_random_spheres") else None
+        big = r.generate_random_spheres(158, install=False)  # the host loop's list, bit for bit, built on the device
         gen = "device (rtw_scene_random_spheres)"
         if big is None:
             R.reseed()

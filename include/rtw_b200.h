@@ -177,6 +177,20 @@ RTW_API int rtw_set_option(rtw_ctx* ctx, int option, int64_t value);
  */
 RTW_API int rtw_set_scene(rtw_ctx* ctx, const float* geom4, const float* mat4, const uint32_t* kind, uint32_t n_spheres);
 
+/*
+ * scene_random_spheres(; elem_type = Float32), src/scenes.jl:49-84, built ON THE DEVICE -- no host loop, so the ~100k-sphere
+ * list of the large configuration takes milliseconds instead of seconds.  The list is the one the reference's sequential
+ * loop produces, bit for bit: `rng_state` is the state (s0, s1) of the calling thread's Xoroshiro128Plus (src/rand.jl:7),
+ * from which the builder draws in whatever state it is; on return it holds the state after the builder's last draw, so
+ * host code that keeps using the same generator continues as after the reference's loop.  half_extent generalises the
+ * `-11:10` grid (reference value 11; 158 gives BASELINE's ~100k spheres).
+ *   install != 0 : the list becomes the scene of the context (as rtw_set_scene);
+ *   geom4 / mat4 / kind (may all be NULL) : host arrays of `capacity` >= n_spheres entries that receive the list.
+ * *n_spheres is always written (4 * half_extent^2 + 4 is an upper bound).
+ */
+RTW_API int rtw_scene_random_spheres(rtw_ctx* ctx, uint64_t rng_state[2], int half_extent, int install, float* geom4,
+                                     float* mat4, uint32_t* kind, uint32_t capacity, uint32_t* n_spheres);
+
 /* ---- the hot path ---------------------------------------------------------------------------- */
 
 /*

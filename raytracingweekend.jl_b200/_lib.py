@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = (
     "rtw_last_error",
     "rtw_set_option",
     "rtw_set_scene",
+    "rtw_scene_random_spheres",
     "rtw_render",
     "rtw_render_scene",
     "rtw_render_rows_device",
@@ -187,6 +188,8 @@ def load() -> C.CDLL:
     lib.rtw_set_option.argtypes = [vp, i32, i64]
     lib.rtw_set_scene.restype = i32
     lib.rtw_set_scene.argtypes = [vp, fp, fp, u32p, u32]
+    lib.rtw_scene_random_spheres.restype = i32
+    lib.rtw_scene_random_spheres.argtypes = [vp, C.POINTER(u64), i32, i32, fp, fp, u32p, u32, u32p]
     lib.rtw_render.restype = i32
     lib.rtw_render.argtypes = [vp, C.POINTER(rtw_camera), i32, i32, i32, u64, fp, C.POINTER(rtw_stats)]
     lib.rtw_render_scene.restype = i32

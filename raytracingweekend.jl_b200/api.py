@@ -116,6 +116,26 @@ class Renderer:
                                             kind.ctypes.data_as(C.POINTER(C.c_uint32)), len(kind)))
         self.n_spheres = len(kind)
 
+    def generate_random_spheres(self, half_extent: int = 11, *, install: bool = True, rng=None):
+        """scene_random_spheres(; elem_type=Float32), src/scenes.jl:49-84, built on the device (no host loop): the same
+        list, bit for bit, as host.scene_random_spheres(half_extent=...) drawing from `rng` (default: the calling
+        thread's TRNG[0]), whose state advances exactly as the host loop would advance it.  Returns the flattened
+        (geom4, mat4, kind); with install=True the list also becomes the scene of this context."""
+        from .host import TRNG
+        g = rng if rng is not None else TRNG[0]
+        state = (C.c_uint64 * 2)(g.x, g.y)
+        cap = 4 * int(half_extent) * int(half_extent) + 4
+        geom = np.zeros((cap, 4), dtype=F32)
+        mat = np.zeros((cap, 4), dtype=F32)
+        kind = np.zeros(cap, dtype=np.uint32)
+        n = C.c_uint32()
+        self._check(self._lib.rtw_scene_random_spheres(self._ctx, state, int(half_extent), 1 if install else 0, _fp(geom),
+                                                       _fp(mat), kind.ctypes.data_as(C.POINTER(C.c_uint32)), cap, C.byref(n)))
+        g.x, g.y = int(state[0]), int(state[1])
+        if install:
+            self.n_spheres = n.value
+        return geom[:n.value].copy(), mat[:n.value].copy(), kind[:n.value].copy()
+
     # -- the hot path, host buffers (what the Julia `render` binds to)
     def render(self, cam: Camera, image_width: int = 400, n_samples: int = 1, *, max_depth: int = DEFAULT_MAX_DEPTH,
                seed: int = DEFAULT_SEED, scene=None, out: Optional[np.ndarray] = None) -> np.ndarray:

@@ -7,7 +7,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false
        -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Xptxas -v)
-SRCS=(rtw_kernels rtw_fused2 rtw_f64 rtw_capi rtw_image rtw_wavefront rtw_small)
+SRCS=(rtw_kernels rtw_fused2 rtw_f64 rtw_capi rtw_image rtw_wavefront rtw_small rtw_scenegen)
 # RTW_BUILD_VARIANTS=1: also build the kernel families kept only as measured comparisons (the first fused kernel with
 # its rays-per-lane / sweep variants, the CTA wavefront, 4 cooperating lanes, per-slot candidate walks); their tests are
 # marked `variants`.  The default library ships the default kernel, the split wavefront, the grid mode and Float64.

@@ -69,6 +69,9 @@ struct DeviceState {
     float* d_scratch = nullptr;
     unsigned char* d_wf = nullptr;  // RTW_MODE_WAVEFRONT path pool
     size_t wf_cap = 0;              // bytes
+    // device-side scene generator (rtw_scenegen.cu): work space + the generated list
+    unsigned char* d_gen_ws = nullptr;
+    size_t gen_ws_cap = 0;
     // latency path (rtw_small.cu): image and totals in mapped pinned host memory, device counters kept zero between calls
     float* h_small_img = nullptr;
     size_t small_img_cap = 0;  // floats
@@ -1303,6 +1306,7 @@ int rtw_destroy(rtw_ctx* ctx) {
         cudaFree(ds.d_accum); cudaFree(ds.d_counters); cudaFree(ds.d_tile);
         cudaFree(ds.d_gather); cudaFree(ds.d_image); cudaFree(ds.d_rgb8); cudaFree(ds.d_scratch); cudaFree(ds.d_wf);
         if (ds.h_counters) cudaFreeHost(ds.h_counters);
+        cudaFree(ds.d_gen_ws);
         if (ds.h_small_img) cudaFreeHost(ds.h_small_img);
         if (ds.h_small_tot) cudaFreeHost(ds.h_small_tot);
         for (auto& e : ds.ev) if (e) cudaEventDestroy(e);
@@ -1379,6 +1383,55 @@ int rtw_set_scene(rtw_ctx* ctx, const float* geom4, const float* mat4, const uin
         return set_scene_locked(ctx, geom4, mat4, kind, n_spheres);
     } catch (...) {
         return fail(ctx, RTW_E_INTERNAL, "unexpected C++ exception in rtw_set_scene");
+    }
+}
+
+int rtw_scene_random_spheres(rtw_ctx* ctx, uint64_t rng_state[2], int half_extent, int install, float* geom4, float* mat4,
+                             uint32_t* kind, uint32_t capacity, uint32_t* n_spheres) {
+    if (!ctx) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    try {
+        if (!rng_state || !n_spheres) return fail(ctx, RTW_E_INVALID_ARG, "rng_state / n_spheres is NULL");
+        if (half_extent < 1 || half_extent > 512) return fail(ctx, RTW_E_INVALID_ARG, "half_extent must be in 1..512");
+        DeviceState& ds = ctx->dev[0];
+        RTW_CUDA(ctx, cudaSetDevice(ds.device));
+        const size_t cap = rtw::scenegen_max_spheres(half_extent);
+        const size_t ws = rtw::scenegen_workspace_bytes(half_extent);
+        const size_t list_bytes = cap * (16 + 16 + 4) + 1024;
+        int rc = grow(ctx, &ds.d_gen_ws, &ds.gen_ws_cap, ws + list_bytes);
+        if (rc) return rc;
+        float4* d_g = (float4*)(ds.d_gen_ws + ws);
+        float4* d_m = d_g + cap;
+        uint32_t* d_k = (uint32_t*)(d_m + cap);
+        unsigned long long* h_out = ds.h_counters + kCounters;  // pinned scratch
+        RTW_CUDA(ctx, rtw::launch_scenegen(rng_state[0], rng_state[1], half_extent, ds.d_gen_ws, d_g, d_m, d_k, h_out, ds.stream));
+        RTW_CUDA(ctx, cudaStreamSynchronize(ds.stream));
+        const uint32_t n = (uint32_t)(h_out[2] & 0xffffffffull);
+        *n_spheres = n;
+        if (n > cap) return fail(ctx, RTW_E_INTERNAL, "scene generator produced more spheres than its bound");
+        const bool want_arrays = geom4 || mat4 || kind;
+        if (want_arrays && (!geom4 || !mat4 || !kind || capacity < n))
+            return fail(ctx, RTW_E_INVALID_ARG, "geom4 / mat4 / kind must all be given with capacity >= n_spheres");
+        std::vector<float> hg, hm;
+        std::vector<uint32_t> hk;
+        float* pg = geom4;
+        float* pm = mat4;
+        uint32_t* pk = kind;
+        if (!want_arrays) {
+            hg.resize(4 * (size_t)n); hm.resize(4 * (size_t)n); hk.resize(n);
+            pg = hg.data(); pm = hm.data(); pk = hk.data();
+        }
+        if (want_arrays || install) {
+            RTW_CUDA(ctx, cudaMemcpy(pg, d_g, 16 * (size_t)n, cudaMemcpyDeviceToHost));
+            RTW_CUDA(ctx, cudaMemcpy(pm, d_m, 16 * (size_t)n, cudaMemcpyDeviceToHost));
+            RTW_CUDA(ctx, cudaMemcpy(pk, d_k, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+        }
+        rng_state[0] = h_out[0];
+        rng_state[1] = h_out[1];
+        if (install) return set_scene_locked(ctx, pg, pm, pk, n);
+        return RTW_OK;
+    } catch (...) {
+        return fail(ctx, RTW_E_INTERNAL, "unexpected C++ exception in rtw_scene_random_spheres");
     }
 }
 

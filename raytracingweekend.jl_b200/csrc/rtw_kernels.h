@@ -149,6 +149,11 @@ cudaError_t launch_quantize_rgb8(const float* img, int W, int H, unsigned char* 
 // latency path (rtw_small.cu): a whole small render in one launch; both device counters must be zero on entry
 cudaError_t launch_small_render(const TraceParams& p, double inv_scale, float* out_img, unsigned long long* host_totals,
                                 cudaStream_t stream, LaunchInfo* info);
+// device-side scene_random_spheres (rtw_scenegen.cu)
+size_t scenegen_max_spheres(int half);
+size_t scenegen_workspace_bytes(int half);
+cudaError_t launch_scenegen(unsigned long long s0, unsigned long long s1, int half, void* workspace, float4* geom, float4* mat,
+                            uint32_t* kind, unsigned long long* out_host, cudaStream_t stream);
 // Float64 path (rtw_f64.cu)
 cudaError_t launch_trace_f64(const TraceParams64& p, int num_sms, cudaStream_t stream, LaunchInfo* info);
 cudaError_t launch_resolve_f64(const unsigned long long* accum, int W, int H, int n_rows, int row_start, int row_stride,

@@ -71,3 +71,27 @@ def test_small_render_is_off_for_variants_and_other_modes(rtw, fast, scenes):
     fast.set_option(rtw.RTW_OPT_SMALL_RENDER, 1)
     fast.render(cam, 96, 1)
     assert fast.last_stats["kernel_launches"] == 1
+
+
+@pytest.mark.parametrize("half", [11, 3, 26, 158])
+def test_device_scene_generator_reproduces_the_host_builder(rtw, fast, half):
+    # scene_random_spheres (src/scenes.jl:49-84) built on the device: the same list, bit for bit, as the sequential host
+    # loop (host.py mirrors the reference's loop and its Xoroshiro128Plus stream), and the same generator state after it
+    rtw.reseed()
+    for _ in range(5):
+        rtw.trand()  # "draws from the calling thread's TRNG in whatever state it is"
+    x0, y0 = rtw.TRNG[0].x, rtw.TRNG[0].y
+    g_ref, m_ref, k_ref = rtw.flatten_scene(rtw.scene_random_spheres(half_extent=half))
+    after = (rtw.TRNG[0].x, rtw.TRNG[0].y)
+    rtw.TRNG[0].x, rtw.TRNG[0].y = x0, y0
+    g, m, k = fast.generate_random_spheres(half)
+    assert (rtw.TRNG[0].x, rtw.TRNG[0].y) == after
+    assert len(k) == len(k_ref) and fast.n_spheres == len(k)
+    assert np.array_equal(k, k_ref)
+    assert np.array_equal(g.view(np.uint32), g_ref.view(np.uint32))
+    assert np.array_equal(m.view(np.uint32), m_ref.view(np.uint32))
+    # the generated list is installed: rendering it equals rendering the host-built one
+    cam = rtw.t_cam1()
+    a = np.array(fast.render(cam, 64, 2, max_depth=8))
+    b = np.array(fast.render(cam, 64, 2, max_depth=8, scene=(g_ref, m_ref, k_ref)))
+    assert np.array_equal(a, b)

@@ -5,7 +5,9 @@
 # materials, HittableList (src/structs.jl, src/material.jl) and the scene builders (src/scenes.jl).  This module
 # adds one method, `render_b200`, with the positional signature of the reference's
 #     render(scene::HittableList, cam::Camera{T}, image_width=400, n_samples=1)          src/render.jl:8-9
-# and can `import RayTracingWeekend: render` + overload it for Camera{Float32} to be a true drop-in (see the end).
+# and `RayTracingWeekendB200.install!()` makes it THE method: it defines `RayTracingWeekend.render` for
+# Camera{Float32} / Camera{Float64}, so existing scripts (`render(scene_random_spheres(; elem_type=Float32), cam, 1920,
+# 1000)`) run on the GPUs unchanged.  Opt-in, because it replaces a method of another package.
 #
 # NOTE: Julia is not installed in the build image, so this file is exercised only where `julia` exists; the
 # Python package next to it (api.py) makes the identical sequence of C-ABI calls and is what the tests drive.
@@ -37,6 +39,24 @@ struct RtwStats
     ms_resolve::Float32
     ms_h2d::Float32
     ms_d2h::Float32
+    n_devices::Int32            # ABI v3
+    reserved0::Int32
+    grid_fallback_rays::UInt64
+    grid_loose_cells::UInt64
+end
+
+const RTW_ABI_VERSION = 3
+
+# The ABI passes Julia's own structs: check the layouts once, when the module loads (include/rtw_b200.h:
+# rtw_camera = 22 x f32, rtw_camera_f64 = 22 x f64, rtw_stats = 88 bytes) and that the library speaks this ABI.
+function __init__()
+    @assert isbitstype(Camera{Float32}) && sizeof(Camera{Float32}) == 88 "Camera{Float32} is not the 22 x Float32 the ABI expects"
+    @assert isbitstype(Camera{Float64}) && sizeof(Camera{Float64}) == 176 "Camera{Float64} is not the 22 x Float64 the ABI expects"
+    @assert fieldnames(Camera{Float32}) == (:origin, :lower_left_corner, :horizontal, :vertical, :u, :v, :w, :lens_radius)
+    @assert sizeof(RtwStats) == 88 "RtwStats does not match rtw_stats"
+    @assert sizeof(RGB{Float32}) == 12 && sizeof(RGB{Float64}) == 24
+    v = ccall((:rtw_abi_version, librtw), Cint, ())
+    v == RTW_ABI_VERSION || error("librtw_b200.so has ABI version $v, this shim was written for $RTW_ABI_VERSION")
 end
 
 mutable struct Context
@@ -65,10 +85,23 @@ function Context(devices::Vector{<:Integer} = [0])
 end
 
 # rtw_set_option: e.g. `set_option!(ctx, RTW_OPT_MODE, RTW_MODE_GRID)` renders the same image bits through a uniform grid
-# (2.7x faster on scene_random_spheres, ~400x on 100k spheres); the default is the reference's linear sweep
-const RTW_OPT_MODE  = Cint(1)
-const RTW_MODE_FUSED = 0
-const RTW_MODE_GRID  = 3
+# (2.3x faster on scene_random_spheres, ~140x on 100k spheres); the default is the reference's linear sweep
+const RTW_OPT_MODE            = Cint(1)   # RTW_MODE_*
+const RTW_OPT_BLOCKS_PER_SM   = Cint(3)
+const RTW_OPT_COLLECT_TIMING  = Cint(4)
+const RTW_OPT_RAYS_PER_LANE   = Cint(5)   # options 5-9 select kernel variants: need a library built with RTW_BUILD_VARIANTS=1
+const RTW_OPT_SWEEP           = Cint(6)
+const RTW_OPT_COOP            = Cint(7)
+const RTW_OPT_TAIL            = Cint(8)
+const RTW_OPT_WALK            = Cint(9)
+const RTW_OPT_GATHER          = Cint(10)  # RTW_GATHER_*: framebuffer gather of a multi-device context
+const RTW_OPT_SMALL_RENDER    = Cint(11)  # 1 (default): small renders take the single-launch latency path
+const RTW_MODE_FUSED          = 0         # the reference's linear sweep (default, the benchmarked path)
+const RTW_MODE_WAVEFRONT      = 1         # separate raygen / intersect / shade / accumulate kernels
+const RTW_MODE_CTA_WAVEFRONT  = 2         # (RTW_BUILD_VARIANTS=1)
+const RTW_MODE_GRID           = 3         # uniform-grid traversal, same image bits for every list size
+const RTW_GATHER_PEER         = 0
+const RTW_GATHER_NCCL         = 1
 set_option!(ctx::Context, option::Integer, value::Integer) =
     check(ctx.ptr, ccall((:rtw_set_option, librtw), Cint, (Ptr{Cvoid}, Cint, Int64), ctx.ptr, option, value))
 
@@ -230,11 +263,72 @@ function load_scene(path::AbstractString)
     scene
 end
 
-# To make it a true drop-in, overload the reference's method for Float32 cameras:
-#     import RayTracingWeekend: render
-#     render(scene::HittableList, cam::Union{Camera{Float32},Camera{Float64}}, image_width=400, n_samples=1) =
-#         RayTracingWeekendB200.render_b200(scene, cam, image_width, n_samples)
+# ---- scene_random_spheres on the device (src/scenes.jl:49-84; rtw_scene_random_spheres) ---------------------------------
+"""
+    scene_random_spheres_device!(ctx = default_context(); half_extent = 11, rng = TRNG[Threads.threadid()])
 
-export render_b200, Context, RtwStats, set_option!, RTW_OPT_MODE, RTW_MODE_FUSED, RTW_MODE_GRID, set_scene!, accumulate!, resolve, save_png, save_scene, load_scene
+Builds `scene_random_spheres(; elem_type=Float32)` on the GPU -- the list the reference's loop would produce from `rng`
+in its current state, bit for bit, with `rng` advanced exactly as the loop would advance it -- installs it as the scene of
+`ctx` (render it with `render_resident`) and returns it as a HittableList.  `half_extent = 158` gives ~100k spheres in
+milliseconds instead of the seconds of the host loop.
+"""
+function scene_random_spheres_device!(ctx::Context = default_context(); half_extent::Integer = 11,
+                                      rng = RayTracingWeekend.TRNG[Threads.threadid()])
+    cap = 4 * half_extent^2 + 4
+    geom, mat, kind = Matrix{Float32}(undef, 4, cap), Matrix{Float32}(undef, 4, cap), Vector{UInt32}(undef, cap)
+    state = UInt64[rng.x, rng.y]          # Xoroshiro128Plus holds its state in the fields x, y (RandomNumbers.jl 1.5.3)
+    n = Ref{UInt32}(0)
+    GC.@preserve geom mat kind state check(ctx.ptr, ccall((:rtw_scene_random_spheres, librtw), Cint,
+        (Ptr{Cvoid}, Ptr{UInt64}, Cint, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{UInt32}, UInt32, Ptr{UInt32}),
+        ctx.ptr, state, half_extent, 1, geom, mat, kind, cap, n))
+    rng.x, rng.y = state[1], state[2]
+    scene = HittableList()
+    for k in 1:Int(n[])
+        albedo = SA[mat[1, k], mat[2, k], mat[3, k]]
+        m = kind[k] == RTW_LAMBERTIAN ? Lambertian(albedo) :
+            kind[k] == RTW_METAL ? Metal(albedo, mat[4, k]) : Dielectric(mat[4, k])
+        push!(scene, Sphere(SA[geom[1, k], geom[2, k], geom[3, k]], geom[4, k], m))
+    end
+    scene
+end
+
+"`render` of the scene already resident in `ctx` (rtw_set_scene / scene_random_spheres_device!): rtw_render"
+function render_resident(ctx::Context, cam::Camera{Float32}, image_width::Integer = 400, n_samples::Integer = 1;
+                         max_depth::Integer = 16, seed::Integer = 1)
+    H = Int(ccall((:rtw_image_height, librtw), Cint, (Cint,), image_width))
+    img = Matrix{RGB{Float32}}(undef, H, image_width)
+    st = Ref{RtwStats}()
+    camref = Ref(cam)
+    GC.@preserve img camref check(ctx.ptr, ccall((:rtw_render, librtw), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, UInt64, Ptr{Cvoid}, Ptr{RtwStats}),
+        ctx.ptr, camref, image_width, n_samples, max_depth, seed, img, st))
+    img
+end
+
+# ---- the drop-in --------------------------------------------------------------------------------------------------------
+"""
+    RayTracingWeekendB200.install!(; max_depth = 16, seed = 1, ctx = default_context())
+
+Defines `RayTracingWeekend.render(scene::HittableList, cam::Camera{Float32 | Float64}, image_width=400, n_samples=1)`
+(src/render.jl:8-9) as a call into the GPU library, replacing the package's CPU method for those two camera types:
+after this, every script that calls `render(scene, cam, w, n)` runs on the B200s unchanged.  `max_depth` and `seed`
+stand for the two things the reference hard-codes (`ray_color`'s depth of 16, src/ray_color.jl:14; `reseed!()` at the
+top of every render, src/render.jl:21).  Opt-in because it overwrites a method of another package (Julia prints a
+"method overwritten" notice); `uninstall!()` is not possible -- restart Julia to get the CPU method back.
+"""
+function install!(; max_depth::Integer = 16, seed::Integer = 1, ctx::Context = default_context())
+    @eval RayTracingWeekend begin
+        function render(scene::HittableList, cam::Union{Camera{Float32},Camera{Float64}}, image_width = 400, n_samples = 1)
+            $(render_b200)(scene, cam, image_width, n_samples; max_depth = $max_depth, seed = $seed, ctx = $ctx)
+        end
+    end
+    nothing
+end
+
+export render_b200, render_resident, install!, Context, RtwStats, set_option!, set_scene!, accumulate!, resolve, save_png,
+       save_scene, load_scene, scene_random_spheres_device!,
+       RTW_OPT_MODE, RTW_OPT_BLOCKS_PER_SM, RTW_OPT_COLLECT_TIMING, RTW_OPT_RAYS_PER_LANE, RTW_OPT_SWEEP, RTW_OPT_COOP,
+       RTW_OPT_TAIL, RTW_OPT_WALK, RTW_OPT_GATHER, RTW_OPT_SMALL_RENDER, RTW_MODE_FUSED, RTW_MODE_WAVEFRONT,
+       RTW_MODE_CTA_WAVEFRONT, RTW_MODE_GRID, RTW_GATHER_PEER, RTW_GATHER_NCCL
 
 end # module

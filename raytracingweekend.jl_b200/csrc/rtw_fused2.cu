@@ -213,13 +213,36 @@ __device__ __forceinline__ void sweep_masks_packed2(uint32_t tile_lane, uint32_t
 //   * the ragged last super-chunk runs the same number of pairs on every lane of a group (ceil(pairs / kCoop), the
 //     tile is zero-padded to a whole super-chunk), unrolled by 4; tests of pairs that do not exist are forced to "miss"
 //     when the mask word is stored.  Lists <= 32 * 32 spheres (kCoop * n_super_chunks <= 32 summary bits).
-template <int kCoop, int kBlock>
-__device__ __forceinline__ uint32_t sweep_masks_packed3(uint32_t tile_lane, uint32_t count, uint32_t coop_h,
-                                                        uint32_t mask_lane, const f3 (&o)[kCoop], const f3 (&d)[kCoop]) {
-    constexpr uint32_t kSuper = 32u * kCoop;
+// what the sweep of a list needs besides the tile: loop-invariant over the bounces, computed once per kernel
+struct SweepPlan {
+    uint32_t nfull;  // whole super-chunks
+    uint32_t run;    // pairs every lane runs in the ragged last super-chunk (0: there is none)
+    uint32_t sh;     // left-alignment of its mask words
+    uint32_t fill;   // bits of its mask words that are forced to "miss" for this lane
+};
+
+template <int kCoop>
+__device__ __forceinline__ SweepPlan make_sweep_plan(uint32_t count, uint32_t coop_h) {
     constexpr uint32_t kSuperPairs = 16u * kCoop;
     const uint32_t npairs = (count + 1u) >> 1;
-    const uint32_t nfull = (count & 1u) ? (npairs - 1u) / kSuperPairs : npairs / kSuperPairs;
+    SweepPlan P;
+    // super-chunks that are complete and do not end in the zero pad partner of an odd last sphere
+    P.nfull = (count & 1u) ? (npairs - 1u) / kSuperPairs : npairs / kSuperPairs;
+    const uint32_t pairs_here = npairs - P.nfull * kSuperPairs;  // 0 .. kSuperPairs
+    P.run = (pairs_here + kCoop - 1u) / kCoop;                  // uniform over the lanes of a group
+    // this lane's real tests: pairs coop_h, coop_h + kCoop, ... < pairs_here; the last of them may end in the pad
+    // partner of an odd last sphere.  Everything after them (zero pairs of the padding, the pad partner) = miss.
+    const uint32_t mine = pairs_here > coop_h ? (pairs_here - coop_h + kCoop - 1u) / kCoop : 0u;
+    const uint32_t real = 2u * mine - (((count & 1u) != 0u && mine != 0u && coop_h == (pairs_here - 1u) % kCoop) ? 1u : 0u);
+    P.sh = 32u - 2u * P.run;           // left-align the `2 * run` tests that were executed (run >= 1 where it is used)
+    P.fill = low_mask(32u - real);     // bits below the `real` top ones
+    return P;
+}
+
+template <int kCoop, int kBlock>
+__device__ __forceinline__ uint32_t sweep_masks_packed3(uint32_t tile_lane, const SweepPlan plan, uint32_t mask_lane,
+                                                        const f3 (&o)[kCoop], const f3 (&d)[kCoop]) {
+    const uint32_t nfull = plan.nfull;
     uint32_t summary = 0u;
     uint32_t a = tile_lane, ma = mask_lane, bit = 1u;
     for (uint32_t c = 0; c < nfull; ++c) {
@@ -243,12 +266,11 @@ __device__ __forceinline__ uint32_t sweep_masks_packed3(uint32_t tile_lane, uint
         ma += kCoop * kBlock * 4u;
         bit <<= kCoop;
     }
-    const uint32_t pairs_here = npairs - nfull * kSuperPairs;  // 0 .. kSuperPairs
-    if (pairs_here != 0u) {
+    const uint32_t run = plan.run;  // pairs every lane runs in the ragged last super-chunk (uniform), 0 .. 16
+    if (run != 0u) {
         uint32_t m[kCoop];
 #pragma unroll
         for (int r = 0; r < kCoop; ++r) m[r] = 0u;
-        const uint32_t run = (pairs_here + kCoop - 1u) / kCoop;  // pairs every lane runs (uniform), 1 .. 16
         uint32_t i = 0;
         for (; i + 4u <= run; i += 4u) {
 #pragma unroll
@@ -260,15 +282,9 @@ __device__ __forceinline__ uint32_t sweep_masks_packed3(uint32_t tile_lane, uint
             test_pair_packed<kCoop>(lds128(a), lds128(a + 16u), o, d, m);
             a += kCoop * 32u;
         }
-        // this lane's real tests: pairs coop_h, coop_h + kCoop, ... < pairs_here; the last of them may end in the pad
-        // partner of an odd last sphere.  Everything after them (zero pairs of the padding, the pad partner) = miss.
-        const uint32_t mine = pairs_here > coop_h ? (pairs_here - coop_h + kCoop - 1u) / kCoop : 0u;
-        const uint32_t real = 2u * mine - (((count & 1u) != 0u && mine != 0u && coop_h == (pairs_here - 1u) % kCoop) ? 1u : 0u);
-        const uint32_t sh = 32u - 2u * run;            // left-align the `2 * run` tests that were executed
-        const uint32_t fill = low_mask(32u - real);    // bits below the `real` top ones
 #pragma unroll
         for (int r = 0; r < kCoop; ++r) {
-            m[r] = (sh >= 32u ? 0u : (m[r] << sh)) | fill;
+            m[r] = (m[r] << plan.sh) | plan.fill;
             sts32(ma + (uint32_t)r * (kBlock * 4u), m[r]);
             summary |= m[r] != 0xffffffffu ? (bit << r) : 0u;
         }
@@ -471,6 +487,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) fused_trace2_kernel(const 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     uint4* const coop_slot = s_coop[threadIdx.x >> 5];
+    const SweepPlan plan = make_sweep_plan<kCoop>(n, threadIdx.x & (kCoop - 1));
 
     // path state of the lane
     f3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 1.f, 0.f);
@@ -717,8 +734,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) fused_trace2_kernel(const 
             uint32_t summary[kCoop];
             exchange_rays<kCoop>(o, d, alive, so, sd, sa);
             if (!kMulti && kOwnWalk) {
-                const uint32_t sum1 = sweep_masks_packed3<kCoop, kBlock>(smem_u32(s_tile0) + h * 32u, n, h,
-                                                                              smem_u32(s_mask), so, sd);
+                const uint32_t sum1 = sweep_masks_packed3<kCoop, kBlock>(smem_u32(s_tile0) + h * 32u, plan,
+                                                                         smem_u32(s_mask), so, sd);
                 walk_own_ray_perm<kCoop, kBlock>(s_tile1, s_mask - threadIdx.x, o, d, alive, sum1, best_t, best_k);
             } else if (!kMulti) {
                 sweep_masks_packed2<kCoop, kCoop, kBlock>(smem_u32(s_tile0) + h * 32u, n, h, smem_u32(s_mask), so, sd,

@@ -860,3 +860,27 @@ def test_grid_mode_large_soups_are_exact(rtw, oracle, renderer, n):
     assert sweep > 0, "no ray reached the whole-list sweep: the set does not exercise tier 3"
     if n >= 20000:
         assert loose > 0, "no ray used the loose registration: the set does not exercise tier 2"
+
+
+def test_multi_device_gather_peer_and_nccl_identical(rtw, scenes):
+    # one context over several devices: rows r -> device r mod G, tiles collected on device 0 by peer copies (default)
+    # or by ONE grouped ncclSend/ncclRecv (RTW_GATHER_NCCL, the north-star's "single NCCL gather").  Needs >= 2 GPUs.
+    import ctypes as C
+    n = C.c_int()
+    rtw._lib.load().rtw_device_count(C.byref(n))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs")
+    cam = rtw.t_cam1()
+    with rtw.Renderer([0]) as r1:
+        a = np.array(r1.render(cam, 400, 8, max_depth=16, scene=scenes["random"]))
+        seg1 = r1.last_stats["ray_segments"]
+    G = min(n.value, 8)
+    with rtw.Renderer(list(range(G))) as rn:
+        b = np.array(rn.render(cam, 400, 8, max_depth=16, scene=scenes["random"]))
+        assert rn.last_stats["n_devices"] == G and rn.last_stats["ray_segments"] == seg1
+        rn.set_option(rtw.RTW_OPT_GATHER, rtw.RTW_GATHER_NCCL)
+        c = np.array(rn.render(cam, 400, 8, max_depth=16, scene=scenes["random"]))
+        c2 = np.array(rn.render(cam, 403, 3, max_depth=16, scene=scenes["random"]))  # ragged: H = 226 rows over G devices
+        rn.set_option(rtw.RTW_OPT_GATHER, rtw.RTW_GATHER_PEER)
+        b2 = np.array(rn.render(cam, 403, 3, max_depth=16, scene=scenes["random"]))
+    assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(b2, c2)

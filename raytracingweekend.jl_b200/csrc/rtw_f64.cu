@@ -191,11 +191,15 @@ __global__ void __launch_bounds__(kTraceBlock, 3) trace_f64_kernel(const __grid_
             uint32_t* mp = s_mask;
             for (uint32_t c = 0; c < nfull; ++c) {
                 uint32_t m0 = 0u, m1 = 0u;
+                // 16 spheres per unrolled body: the 32-sphere body (847 instructions) overflowed the instruction cache
+#pragma unroll 1
+                for (int jb = 0; jb < 64; jb += 32) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const double4 s = lp[2 * j];
-                    m0 = __funnelshift_l(disc_hi(s, o, d), m0, 1);  // test j ends at bit 31 - j; set = miss
-                    m1 = __funnelshift_l(disc_hi(s, o1, d1), m1, 1);
+                    for (int j = 0; j < 16; ++j) {
+                        const double4 s = lp[jb + 2 * j];
+                        m0 = __funnelshift_l(disc_hi(s, o, d), m0, 1);  // test j ends at bit 31 - j; set = miss
+                        m1 = __funnelshift_l(disc_hi(s, o1, d1), m1, 1);
+                    }
                 }
                 mp[0] = m0;
                 mp[kTraceBlock] = m1;
@@ -298,13 +302,15 @@ __global__ void __launch_bounds__(kTraceBlock, 3) trace_f64_kernel(const __grid_
                 const bool front = dotd(d, on) < 0.0;                                                  // hit.jl:7
                 const d3 nn = front ? on : mkd(-on.x, -on.y, -on.z);
                 d3 nd;
-                if (kind == 0u) {  // Lambertian, src/material.jl:13-23
-                    const d3 rv = unit_vector_d(rng, nhits, k0, k1);
+                // Lambertian (src/material.jl:13-23) and Metal (:31-34) both draw one unit vector first (Metal even when
+                // fuzz == 0): ONE rejection loop for the two materials keeps their lanes together
+                d3 rv = mkd(0.0, 0.0, 0.0);
+                if (kind != 2u) rv = unit_vector_d(rng, nhits, k0, k1);
+                if (kind == 0u) {  // Lambertian
                     const d3 sd = mkd(nn.x + rv.x, nn.y + rv.y, nn.z + rv.z);
                     nd = dotd(sd, sd) < 1e-5 ? nn : normalized(sd);  // near_zero, src/vec.jl:20
-                } else if (kind == 1u) {  // Metal, src/material.jl:31-34
+                } else if (kind == 1u) {  // Metal
                     const d3 refl = reflectd(d, nn);
-                    const d3 rv = unit_vector_d(rng, nhits, k0, k1);
                     nd = normalized(mkd(fma(m.w, rv.x, refl.x), fma(m.w, rv.y, refl.y), fma(m.w, rv.z, refl.z)));
                 } else {  // Dielectric, src/material.jl:41-53
                     const double ratio = front ? 1.0 / m.w : m.w;

@@ -43,19 +43,30 @@ __device__ __forceinline__ d3 reflectd(d3 v, d3 n) {  // src/light.jl:6
     return mkd(fma(-k, n.x, v.x), fma(-k, n.y, v.y), fma(-k, n.z, v.z));
 }
 
-// normalize(random_vec3_in_sphere), src/rand.jl:15-22,29
-__device__ __forceinline__ d3 unit_vector_d(const PathRng& g, uint32_t event, uint32_t k0, uint32_t k1) {
-    for (uint32_t a = 0;; ++a) {
-        const u32x4 b0 = philox_block(g, event, 2u * a, k0, k1);
-        const u32x4 b1 = philox_block(g, event, 2u * a + 1u, k0, k1);
-        const d3 p = mkd(pm1d(b0.w0, b0.w1), pm1d(b0.w2, b0.w3), pm1d(b1.w0, b1.w1));
-        if (dotd(p, p) <= 1.0) return normalized(p);
-    }
-}
+// cooperative rejection sampling: with `cnt` lanes in need, each gets per = 32 / cnt helper lanes;
+// entry = per | (ceil(256 / per) << 8), so that lane / per = (lane * (entry >> 8)) >> 8 for lane < 32
+__constant__ uint32_t c_coop_tab64[33] = {
+    0u,
+    32u | (8u << 8), 16u | (16u << 8), 10u | (26u << 8), 8u | (32u << 8), 6u | (43u << 8), 5u | (52u << 8),
+    4u | (64u << 8), 4u | (64u << 8), 3u | (86u << 8), 3u | (86u << 8), 2u | (128u << 8), 2u | (128u << 8),
+    2u | (128u << 8), 2u | (128u << 8), 2u | (128u << 8), 2u | (128u << 8), 1u | (256u << 8), 1u | (256u << 8),
+    1u | (256u << 8), 1u | (256u << 8), 1u | (256u << 8), 1u | (256u << 8), 1u | (256u << 8), 1u | (256u << 8),
+    1u | (256u << 8), 1u | (256u << 8), 1u | (256u << 8), 1u | (256u << 8), 1u | (256u << 8), 1u | (256u << 8),
+    1u | (256u << 8), 1u | (256u << 8)};
 
+__device__ __forceinline__ double shfl_d(double v, uint32_t src) { return __shfl_sync(kFullMask, v, (int)src); }
+
+// The loop is laid out like the Float32 kernel's (rtw_fused2.cu): classify + accumulate the paths that ended ->
+// regenerate (idle lanes take the next ticket) -> blocks 0 and 1 of the event's stream for EVERY lane at once (scatter
+// draws of the continuing lanes, primary-ray draws of the new ones) -> warp-cooperative rejection sampling (the stream is
+// addressed, so attempt a of a path can be evaluated by any lane; a lane takes its first accepted attempt in stream
+// order) -> one normalize() for unit(ball sample) | primary direction, one for the scattered direction of all three
+// materials -> closest-hit sweep.  The first Float64 kernel ran each state's code by itself: the two rejection loops
+// alone were 650 of its 8500 issued instructions per bounce, at 3-6 active lanes.
 template <bool kShared>
 __global__ void __launch_bounds__(kTraceBlock, 3) trace_f64_kernel(const __grid_constant__ TraceParams64 P) {
     extern __shared__ __align__(16) unsigned char smem_raw64[];
+    __shared__ __align__(16) uint4 s_coop[kTraceBlock / 32][32];  // rejection-sampling requests of a warp
     double4* s_geom = reinterpret_cast<double4*>(smem_raw64);
     const uint32_t n = P.n_spheres;
     // kShared: one 32-test candidate mask per chunk and lane, behind the list (word c of a lane at (c * block + tid))
@@ -69,6 +80,7 @@ __global__ void __launch_bounds__(kTraceBlock, 3) trace_f64_kernel(const __grid_
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t k0 = P.key0, k1 = P.key1;
     const double tmin = 1e-4;  // T(1e-4), src/ray_color.jl:19
+    uint4* const coop_slot = s_coop[threadIdx.x >> 5];
 
     d3 o = mkd(0, 0, 0), d = mkd(0, 1, 0);
     double thr_r = 1.0, thr_g = 1.0, thr_b = 1.0;
@@ -78,14 +90,39 @@ __global__ void __launch_bounds__(kTraceBlock, 3) trace_f64_kernel(const __grid_
     uint32_t seg_count = 0;
     unsigned long long pool_next = 0, pool_end = 0;
     bool exhausted = false;
+    double best_t = __longlong_as_double(0x7ff0000000000000ll);  // typemax(T)
+    int best_k = -1;
 
     for (;;) {
+        // ---- classify + accumulate the paths that ended
+        bool cont = false;
+        uint32_t kind = 0u;
+        if (alive) {
+            seg_count += 1;
+            if (best_k < 0) {  // miss: skycolor, src/ray_color.jl:1-6 (no contraction)
+                const double t = 0.5 * (d.y + 1.0);
+                const double a = 1.0 - t;
+                const double sr = a + t * 0.5, sg = a + t * 0.7, sb = a + t;
+                unsigned long long* acc = P.accum + (unsigned long long)pix_local * 4ull;
+                atomicAdd(acc + 0, (unsigned long long)__double2ll_rn(thr_r * sr * P.fx_scale));
+                atomicAdd(acc + 1, (unsigned long long)__double2ll_rn(thr_g * sg * P.fx_scale));
+                atomicAdd(acc + 2, (unsigned long long)__double2ll_rn(thr_b * sb * P.fx_scale));
+                alive = false;
+            } else if (++nhits == (uint32_t)P.max_depth) {
+                alive = false;  // the next ray_color call returns black, src/ray_color.jl:15-17
+            } else {
+                cont = true;
+                kind = __ldg(P.kind + best_k);
+            }
+        }
         // ---- regenerate: idle lanes take the next path ticket (src/render.jl:24-37)
+        bool newp = false;
+        double su = 0.0, sv = 0.0;
+        uint32_t s0 = 0u, pl = 0u;
         {
             bool want = !alive && !done;
             unsigned pending = __ballot_sync(kFullMask, want);
             unsigned long long ticket = 0;
-            bool got = false;
             while (pending) {
                 if (exhausted) {
                     if (want) { done = true; want = false; }
@@ -101,54 +138,157 @@ __global__ void __launch_bounds__(kTraceBlock, 3) trace_f64_kernel(const __grid_
                 }
                 const unsigned avail = (unsigned)(pool_end - pool_next);
                 const unsigned rank = __popc(pending & lt_mask);
-                if (want && rank < avail) { ticket = pool_next + rank; want = false; got = true; }
+                if (want && rank < avail) { ticket = pool_next + rank; want = false; newp = true; }
                 const unsigned npend = __popc(pending);
                 pool_next += npend < avail ? npend : avail;
                 pending = __ballot_sync(kFullMask, want);
             }
-            if (got) {
+            if (newp) {
                 const unsigned long long q = ticket / (unsigned)P.spp;
-                const uint32_t pl = (uint32_t)q;
-                const uint32_t s0 = (uint32_t)(ticket - q * (unsigned)P.spp) + (uint32_t)P.sample_first;
+                pl = (uint32_t)q;
+                s0 = (uint32_t)(ticket - q * (unsigned)P.spp) + (uint32_t)P.sample_first;
                 const uint32_t row_local = pl / (uint32_t)P.W, col = pl - row_local * (uint32_t)P.W;
                 const uint32_t i0 = (uint32_t)P.row_start + row_local * (uint32_t)P.row_stride;
-                double s = (double)(col + 1u) / (double)P.W;                  // u = T(j/W), src/render.jl:26
-                double t = (double)((uint32_t)P.H - 1u - i0) / (double)P.H;   // v = T((H-i)/H), src/render.jl:27
+                su = (double)(col + 1u) / (double)P.W;                  // u = T(j/W), src/render.jl:26
+                sv = (double)((uint32_t)P.H - 1u - i0) / (double)P.H;   // v = T((H-i)/H), src/render.jl:27
                 rng.pixel = i0 * (uint32_t)P.W + col;
                 rng.sample = s0;
-                if (s0 != 0u) {  // src/render.jl:30-36: the first sample is centred; du = draw 0, dv = draw 1
-                    const u32x4 b = philox_block(rng, 0u, 0u, k0, k1);
-                    s += u01d(b.w0, b.w1) / (double)(float)P.W;
-                    t += u01d(b.w2, b.w3) / (double)(float)P.H;
-                }
-                // get_ray, src/camera.jl:43-48; random_vec2_in_disk (src/rand.jl:31-38) is always drawn
-                double px, py;
-                for (uint32_t k = 0;; ++k) {
-                    const u32x4 b = philox_block(rng, 0u, 1u + k, k0, k1);
-                    px = pm1d(b.w0, b.w1);
-                    py = pm1d(b.w2, b.w3);
-                    if (fma(py, py, px * px) <= 1.0) break;
-                }
-                const DevCamera64& c = P.cam;
-                const double rx = c.lens_radius * px, ry = c.lens_radius * py;
-                const d3 off = mkd(fma(c.v[0], ry, c.u[0] * rx), fma(c.v[1], ry, c.u[1] * rx), fma(c.v[2], ry, c.u[2] * rx));
-                o = mkd(c.origin[0] + off.x, c.origin[1] + off.y, c.origin[2] + off.z);
-                d3 q3;
-                q3.x = fma(t, c.vertical[0], fma(s, c.horizontal[0], c.llc[0])) - c.origin[0] - off.x;
-                q3.y = fma(t, c.vertical[1], fma(s, c.horizontal[1], c.llc[1])) - c.origin[1] - off.y;
-                q3.z = fma(t, c.vertical[2], fma(s, c.horizontal[2], c.llc[2])) - c.origin[2] - off.z;
-                d = normalized(q3);
-                thr_r = thr_g = thr_b = 1.0;
-                nhits = 0u;
-                pix_local = pl;
-                alive = true;
             }
         }
-        if (__ballot_sync(kFullMask, alive) == 0u) break;
+        if (__ballot_sync(kFullMask, cont || newp) == 0u) break;
+
+        // ---- blocks 0 and 1 of the event for every lane at once
+        // continuing lanes: event = index of this hit -- ball attempt 0 = draws 0, 1, 2 (block 0, block 1 words 0-1), the
+        // dielectric coin = draw 3 (block 1 words 2-3); new lanes: event 0 -- jitter = draws 0, 1 (block 0), disk attempt 0 =
+        // draws 2, 3 (block 1)
+        const uint32_t ev = cont ? nhits : 0u;
+        double px, py, pz = 0.0, coin = 0.0;
+        bool need = false;
+        {
+            const u32x4 b0 = philox_block(rng, ev, 0u, k0, k1);
+            const u32x4 b1 = philox_block(rng, ev, 1u, k0, k1);
+            if (newp) {
+                if (s0 != 0u) {  // src/render.jl:30-36: the first sample is centred; du = draw 0, dv = draw 1
+                    su += u01d(b0.w0, b0.w1) / (double)(float)P.W;
+                    sv += u01d(b0.w2, b0.w3) / (double)(float)P.H;
+                }
+                px = pm1d(b1.w0, b1.w1);  // random_vec2_in_disk (src/rand.jl:31-38) is always drawn, src/camera.jl:44
+                py = pm1d(b1.w2, b1.w3);
+                need = !(fma(py, py, px * px) <= 1.0);
+            } else {
+                px = pm1d(b0.w0, b0.w1);
+                py = pm1d(b0.w2, b0.w3);
+                pz = pm1d(b1.w0, b1.w1);
+                coin = u01d(b1.w2, b1.w3);
+                need = cont && kind != 2u && !(dotd(mkd(px, py, pz), mkd(px, py, pz)) <= 1.0);  // src/rand.jl:15-22
+            }
+        }
+        // ---- cooperative rejection sampling: ball attempt a = blocks 2a, 2a+1 of the event; disk attempt a = block 1+a
+        {
+            unsigned needm = __ballot_sync(kFullMask, need);
+            uint32_t tried = 1u;  // attempts evaluated so far; uniform: every needy lane has failed the same attempts
+            while (needm) {
+                const uint32_t cnt = (uint32_t)__popc(needm);
+                const uint32_t tab = c_coop_tab64[cnt];
+                const uint32_t per = tab & 0xffu;  // helper lanes (= attempts evaluated) per needy lane: 32 / cnt
+                const uint32_t rank = (uint32_t)__popc(needm & lt_mask);
+                if (need) coop_slot[rank] = make_uint4(rng.sample, rng.pixel, ev | (newp ? 0x80000000u : 0u), 0u);
+                __syncwarp();
+                const uint32_t hq = (lane * (tab >> 8)) >> 8;  // lane / per: the request this lane helps
+                const uint32_t ha = lane - hq * per;           // and which of its attempts
+                const uint4 tsk = coop_slot[hq < cnt ? hq : 0u];
+                const bool is_disk = (int)tsk.z < 0;
+                const uint32_t att = tried + ha;
+                const PathRng hr{tsk.x, tsk.y};
+                const uint32_t hev = tsk.z & 0x7fffffffu;
+                const u32x4 ba = philox_block(hr, hev, is_disk ? 1u + att : 2u * att, k0, k1);
+                const u32x4 bb = philox_block(hr, hev, 2u * att + 1u, k0, k1);  // third coordinate of a ball attempt
+                const double hx = pm1d(ba.w0, ba.w1), hy = pm1d(ba.w2, ba.w3);
+                const double hz = is_disk ? 0.0 : pm1d(bb.w0, bb.w1);
+                // disk: fma(y, y, x*x) (src/rand.jl:31-38); ball: dot = fma(z, z, fma(y, y, x*x)) -- with z = 0 the same value
+                const bool ok = (hq < cnt) & (fma(hz, hz, fma(hy, hy, hx * hx)) <= 1.0);
+                const unsigned okm = __ballot_sync(kFullMask, ok);
+                const uint32_t first = rank * per;
+                const uint32_t mine = need ? ((okm >> first) & (per >= 32u ? 0xffffffffu : ((1u << per) - 1u))) : 0u;
+                const uint32_t src = mine ? first + (uint32_t)__ffs((int)mine) - 1u : lane;
+                const double gx = shfl_d(hx, src), gy = shfl_d(hy, src), gz = shfl_d(hz, src);
+                if (mine) { px = gx; py = gy; pz = gz; need = false; }
+                tried += per;
+                needm = __ballot_sync(kFullMask, need);
+                __syncwarp();  // every lane has read its request before the next pass overwrites the slots
+            }
+        }
+        // ---- new lanes: get_ray, src/camera.jl:43-48
+        d3 v1 = mkd(px, py, pz);  // continuing Lambertian / Metal lanes: the point in the unit ball
+        d3 o_new = o;
+        if (newp) {
+            const DevCamera64& c = P.cam;
+            const double rx = c.lens_radius * px, ry = c.lens_radius * py;
+            const d3 off = mkd(fma(c.v[0], ry, c.u[0] * rx), fma(c.v[1], ry, c.u[1] * rx), fma(c.v[2], ry, c.u[2] * rx));
+            o_new = mkd(c.origin[0] + off.x, c.origin[1] + off.y, c.origin[2] + off.z);
+            v1.x = fma(sv, c.vertical[0], fma(su, c.horizontal[0], c.llc[0])) - c.origin[0] - off.x;
+            v1.y = fma(sv, c.vertical[1], fma(su, c.horizontal[1], c.llc[1])) - c.origin[1] - off.y;
+            v1.z = fma(sv, c.vertical[2], fma(su, c.horizontal[2], c.llc[2])) - c.origin[2] - off.z;
+        }
+        const d3 n1 = normalized(v1);  // unit(ball sample) | primary direction: one instance for both
+        // ---- continuing lanes: HitRecord + scatter
+        d3 v2 = mkd(1.0, 0.0, 0.0);  // direction before the final normalize
+        d3 alt = v2;                 // direction used as is (near-zero Lambertian, reflecting Dielectric)
+        bool use_alt = false;
+        if (cont) {
+            const double4 g = P.geom[best_k];
+            const double4 m = P.mat[best_k];
+            const d3 p = mkd(fma(best_t, d.x, o.x), fma(best_t, d.y, o.y), fma(best_t, d.z, o.z));  // hit.jl:3
+            const d3 on = mkd((p.x - g.x) / g.w, (p.y - g.y) / g.w, (p.z - g.z) / g.w);             // hit.jl:33
+            const bool front = dotd(d, on) < 0.0;                                                  // hit.jl:7
+            const d3 nn = front ? on : mkd(-on.x, -on.y, -on.z);
+            if (kind == 0u) {  // Lambertian, src/material.jl:13-23
+                v2 = mkd(nn.x + n1.x, nn.y + n1.y, nn.z + n1.z);
+                use_alt = dotd(v2, v2) < 1e-5;  // near_zero, src/vec.jl:20
+                alt = nn;
+            } else if (kind == 1u) {  // Metal, src/material.jl:31-34; never absorbs (src/structs.jl:43)
+                const d3 refl = reflectd(d, nn);
+                v2 = mkd(fma(m.w, n1.x, refl.x), fma(m.w, n1.y, refl.y), fma(m.w, n1.z, refl.z));
+            } else {  // Dielectric, src/material.jl:41-53
+                const double ratio = front ? 1.0 / m.w : m.w;
+                const double cos_t = fmin(-dotd(d, nn), 1.0);
+                const double sin_t = sqrt(fma(-cos_t, cos_t, 1.0));
+                double r0 = (1.0 - ratio) / (1.0 + ratio);  // Schlick, src/light.jl:19-25
+                r0 = r0 * r0;
+                const double x = 1.0 - cos_t, x2 = x * x, x4 = x2 * x2;
+                // `||` short-circuits (material.jl:47): the coin is ignored on total internal reflection
+                if (ratio * sin_t > 1.0 || fma(1.0 - r0, x4 * x, r0) > coin) {
+                    use_alt = true;
+                    alt = reflectd(d, nn);  // not re-normalised, src/material.jl:48
+                } else {  // refract, src/light.jl:12-17
+                    const d3 perp = mkd(ratio * fma(cos_t, nn.x, d.x), ratio * fma(cos_t, nn.y, d.y),
+                                        ratio * fma(cos_t, nn.z, d.z));
+                    const double sp = sqrt(fabs(1.0 - dotd(perp, perp)));
+                    v2 = mkd(fma(-sp, nn.x, perp.x), fma(-sp, nn.y, perp.y), fma(-sp, nn.z, perp.z));
+                }
+            }
+            if (kind != 2u) {  // attenuation = albedo (Dielectric: ones)
+                thr_r *= m.x;
+                thr_g *= m.y;
+                thr_b *= m.z;
+            }
+            o = p;
+        }
+        const d3 n2 = normalized(v2);  // one instance for the three materials
+        if (cont) {
+            d = use_alt ? alt : n2;
+        } else if (newp) {
+            o = o_new;
+            d = n1;
+            thr_r = thr_g = thr_b = 1.0;
+            nhits = 0u;
+            pix_local = pl;
+            alive = true;
+        }
 
         // ---- intersect: hit(::HittableList), src/hit.jl:38-50, hit(::Sphere) src/hit.jl:12-35
-        double best_t = __longlong_as_double(0x7ff0000000000000ll);  // typemax(T)
-        int best_k = -1;
+        best_t = __longlong_as_double(0x7ff0000000000000ll);  // typemax(T)
+        best_k = -1;
         // one ray-sphere test with root selection against the running closest t (list order: ties go to the later sphere)
         auto resolve = [&](uint32_t k) {
             const double4 s = list[k];
@@ -278,69 +418,6 @@ __global__ void __launch_bounds__(kTraceBlock, 3) trace_f64_kernel(const __grid_
         }
         if (alive)
             for (; k < n; ++k) resolve(k);  // ragged tail
-        }
-        // ---- shade / scatter / accumulate
-        if (alive) {
-            seg_count += 1;
-            if (best_k < 0) {  // miss: skycolor, src/ray_color.jl:1-6 (no contraction)
-                const double t = 0.5 * (d.y + 1.0);
-                const double a = 1.0 - t;
-                const double sr = a + t * 0.5, sg = a + t * 0.7, sb = a + t;
-                unsigned long long* acc = P.accum + (unsigned long long)pix_local * 4ull;
-                atomicAdd(acc + 0, (unsigned long long)__double2ll_rn(thr_r * sr * P.fx_scale));
-                atomicAdd(acc + 1, (unsigned long long)__double2ll_rn(thr_g * sg * P.fx_scale));
-                atomicAdd(acc + 2, (unsigned long long)__double2ll_rn(thr_b * sb * P.fx_scale));
-                alive = false;
-            } else if (++nhits == (uint32_t)P.max_depth) {
-                alive = false;  // the next ray_color call returns black, src/ray_color.jl:15-17
-            } else {
-                const double4 g = P.geom[best_k];
-                const double4 m = P.mat[best_k];
-                const uint32_t kind = __ldg(P.kind + best_k);
-                const d3 p = mkd(fma(best_t, d.x, o.x), fma(best_t, d.y, o.y), fma(best_t, d.z, o.z));  // hit.jl:3
-                const d3 on = mkd((p.x - g.x) / g.w, (p.y - g.y) / g.w, (p.z - g.z) / g.w);             // hit.jl:33
-                const bool front = dotd(d, on) < 0.0;                                                  // hit.jl:7
-                const d3 nn = front ? on : mkd(-on.x, -on.y, -on.z);
-                d3 nd;
-                // Lambertian (src/material.jl:13-23) and Metal (:31-34) both draw one unit vector first (Metal even when
-                // fuzz == 0): ONE rejection loop for the two materials keeps their lanes together
-                d3 rv = mkd(0.0, 0.0, 0.0);
-                if (kind != 2u) rv = unit_vector_d(rng, nhits, k0, k1);
-                if (kind == 0u) {  // Lambertian
-                    const d3 sd = mkd(nn.x + rv.x, nn.y + rv.y, nn.z + rv.z);
-                    nd = dotd(sd, sd) < 1e-5 ? nn : normalized(sd);  // near_zero, src/vec.jl:20
-                } else if (kind == 1u) {  // Metal
-                    const d3 refl = reflectd(d, nn);
-                    nd = normalized(mkd(fma(m.w, rv.x, refl.x), fma(m.w, rv.y, refl.y), fma(m.w, rv.z, refl.z)));
-                } else {  // Dielectric, src/material.jl:41-53
-                    const double ratio = front ? 1.0 / m.w : m.w;
-                    const double cos_t = fmin(-dotd(d, nn), 1.0);
-                    const double sin_t = sqrt(fma(-cos_t, cos_t, 1.0));
-                    bool reflects = ratio * sin_t > 1.0;
-                    if (!reflects) {  // `||` short-circuits: the coin is drawn only when refraction is possible
-                        const u32x4 b = philox_block(rng, nhits, 1u, k0, k1);
-                        double r0 = (1.0 - ratio) / (1.0 + ratio);  // Schlick, src/light.jl:19-25
-                        r0 = r0 * r0;
-                        const double x = 1.0 - cos_t, x2 = x * x, x4 = x2 * x2;
-                        reflects = fma(1.0 - r0, x4 * x, r0) > u01d(b.w2, b.w3);
-                    }
-                    if (reflects) {
-                        nd = reflectd(d, nn);  // not re-normalised, src/material.jl:48
-                    } else {  // refract, src/light.jl:12-17
-                        const d3 perp = mkd(ratio * fma(cos_t, nn.x, d.x), ratio * fma(cos_t, nn.y, d.y),
-                                            ratio * fma(cos_t, nn.z, d.z));
-                        const double sp = sqrt(fabs(1.0 - dotd(perp, perp)));
-                        nd = normalized(mkd(fma(-sp, nn.x, perp.x), fma(-sp, nn.y, perp.y), fma(-sp, nn.z, perp.z)));
-                    }
-                }
-                if (kind != 2u) {  // attenuation = albedo (Dielectric: ones)
-                    thr_r *= m.x;
-                    thr_g *= m.y;
-                    thr_b *= m.z;
-                }
-                o = p;
-                d = nd;
-            }
         }
     }
     for (int off = 16; off > 0; off >>= 1) seg_count += __shfl_xor_sync(kFullMask, seg_count, off);

@@ -64,7 +64,7 @@ __device__ __forceinline__ double shfl_d(double v, uint32_t src) { return __shfl
 // materials -> closest-hit sweep.  The first Float64 kernel ran each state's code by itself: the two rejection loops
 // alone were 650 of its 8500 issued instructions per bounce, at 3-6 active lanes.
 template <bool kShared>
-__global__ void __launch_bounds__(kTraceBlock, 3) trace_f64_kernel(const __grid_constant__ TraceParams64 P) {
+__global__ void __launch_bounds__(kTraceBlock, 2) trace_f64_kernel(const __grid_constant__ TraceParams64 P) {
     extern __shared__ __align__(16) unsigned char smem_raw64[];
     __shared__ __align__(16) uint4 s_coop[kTraceBlock / 32][32];  // rejection-sampling requests of a warp
     double4* s_geom = reinterpret_cast<double4*>(smem_raw64);

@@ -25,6 +25,8 @@
 extern "C" {
 #endif
 
+/* v3: rtw_stats grew (n_devices, grid counters), rtw_scene_random_spheres, rtw_has_variants, RTW_OPT_GATHER,
+ *     RTW_OPT_SMALL_RENDER; RTW_OPT_STRIP removed; kernel variants need RTW_BUILD_VARIANTS=1 */
 #define RTW_ABI_VERSION 3
 
 #if defined(__GNUC__)
@@ -132,12 +134,17 @@ typedef struct rtw_ctx rtw_ctx;
 #define RTW_MODE_FUSED 0          /* one persistent kernel: raygen -> {intersect, shade} loop -> accumulate */
 #define RTW_MODE_WAVEFRONT 1      /* separate raygen / intersect / shade / accumulate kernels + compaction  */
 #define RTW_MODE_GRID 3           /* the fused kernel with a uniform-grid traversal in place of the linear sweep: the same
-                                     closest hit and image bits from far fewer sphere tests (the reference is brute
-                                     force by design, README.md:30; acceleration structures are its long-term goal,
-                                     README.md:175).  Not the benchmarked path; rtw_stats.sphere_tests still reports
-                                     ray_segments * n_spheres, the tests the linear sweep would have made */
+                                     closest hit and image bits from far fewer sphere tests, for EVERY list size (the
+                                     reference is brute force by design, README.md:30; acceleration structures are its
+                                     long-term goal, README.md:175).  Exact by construction: rays the grid cannot answer
+                                     with certainty -- the reference's a = 1 shortcut and the rounding of its discriminant
+                                     let far spheres grow -- are resolved by an exact cooperative sweep and counted in
+                                     rtw_stats.grid_fallback_rays.  Not the benchmarked path;
+                                     rtw_stats.sphere_tests still reports ray_segments * n_spheres, the tests the linear
+                                     sweep would have made */
 #define RTW_MODE_CTA_WAVEFRONT 2  /* the same stages inside persistent CTAs: path pool + work lists in shared memory
-                                     (lists <= 1024 spheres; larger lists fall back to RTW_MODE_FUSED)        */
+                                     (lists <= 1024 spheres); a measured comparison, only in libraries built with
+                                     RTW_BUILD_VARIANTS=1 (rtw_has_variants)                                    */
 
 /* ---- life cycle ------------------------------------------------------------------------------ */
 
@@ -173,7 +180,12 @@ RTW_API int rtw_set_option(rtw_ctx* ctx, int option, int64_t value);
  *   mat4  : n x {albedo.r, albedo.g, albedo.b, param}    param = fuzz (Metal) | ir (Dielectric) | 0 (Lambertian)
  *   kind  : n x RTW_LAMBERTIAN | RTW_METAL | RTW_DIELECTRIC
  * List order is preserved (ties in t go to the later sphere, src/hit.jl:24-26,44-46).  Host pointers;
- * the library copies and never retains them.
+ * the library copies and never retains them.  Failure-atomic: after an error the context holds no scene.  Passing the
+ * arrays of the scene that is already resident is a no-op (rtw_render_scene does it on every call).
+ * Albedo components must be finite and >= 0 (RTW_E_UNSUPPORTED otherwise).  The per-pixel sums are 64-bit fixed point
+ * with 6 bits (64x) of head-room per path: every albedo <= 1 -- all of the reference's scenes -- can never exceed it; a
+ * scene that uses albedo > 1 as emission is rendered as long as max_albedo^(max_depth - 1) <= 64 and the render call is
+ * refused (RTW_E_UNSUPPORTED) beyond that, instead of saturating silently.
  */
 RTW_API int rtw_set_scene(rtw_ctx* ctx, const float* geom4, const float* mat4, const uint32_t* kind, uint32_t n_spheres);
 

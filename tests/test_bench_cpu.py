@@ -42,3 +42,15 @@ def test_product_arm_needs_a_gpu():
         pytest.skip("a GPU is visible")
     out = _run(["--width", "96", "--spp", "1", "--steps", "1", "--warmup", "0", "--no-cpu-baseline"])
     assert out.returncode != 0 and out.stdout.strip() == ""  # fails loudly: no JSON line, no CPU fallback
+
+
+def test_reference_arm_reports_the_host_it_ran_on():
+    out = _run(["--impl", "reference", "--width", "64", "--spp", "2", "--cpu-spp", "1", "--depth", "4", "--steps", "1",
+                "--warmup", "0"])
+    d = json.loads([ln for ln in out.stdout.splitlines() if ln.strip()][0])
+    host = d["cpu_baseline"]["host"]
+    assert host["affinity"] == len(os.sched_getaffinity(0)) and "cgroup_cpus" in host and host["nproc"] >= 1
+    assert d["cpu_baseline"]["cores"] <= max(host["affinity"], 1)
+    assert "julia" in d and d["julia"]["found"] in (True, False)
+    # the timing build: the same source rebuilt on this host; accepted only if it reproduces the portable build's bits
+    assert "-O3 -march=native" in d["cpu_baseline"]["sample"] or "portable build" in d["cpu_baseline"]["sample"]

@@ -120,3 +120,26 @@ def test_bad_arguments(oracle, rtw, scenes):
         args.update(kw)
         with pytest.raises(ValueError):
             oracle.render(g, m, k, _cam(rtw), args.pop("image_width"), args.pop("n_samples"), **args)
+
+
+def test_thread_count_and_work_sharing_do_not_change_the_image(oracle, rtw):
+    # production stream: every draw is addressed, and the threads are dealt 16-pixel blocks round-robin -- any thread count
+    # gives the same bits, also for a one-row slice of a wide image (what the headline parity tests render)
+    g, m, k = rtw.flatten_scene(rtw.scene_4_spheres())
+    cam = rtw.t_default_cam().as_array()
+    a, _, sa = oracle.render(g, m, k, cam, 200, 3, max_depth=8, seed=5, n_threads=1)
+    b, _, sb = oracle.render(g, m, k, cam, 200, 3, max_depth=8, seed=5, n_threads=7)
+    assert np.array_equal(a, b) and sa["ray_segments"] == sb["ray_segments"]
+    row, _, sr = oracle.render(g, m, k, cam, 200, 3, max_depth=8, seed=5, n_threads=5, row_start=60, row_stride=112)
+    assert np.array_equal(row[60], a[60]) and sr["paths"] == 200 * 3
+
+
+def test_path_trace_records_the_segments_of_a_path(oracle, rtw):
+    g, m, k = rtw.flatten_scene(rtw.scene_2_spheres())
+    cam = rtw.t_default_cam().as_array()
+    rgb, seg = oracle.path(g, m, k, cam, 96, 30, 48, 1, max_depth=6, seed=1)
+    rgb2, tr = oracle.path_trace(g, m, k, cam, 96, 30, 48, 1, max_depth=6, seed=1)
+    assert np.array_equal(rgb, rgb2) and len(tr) == seg
+    assert all(abs(np.dot(r[3:6], r[3:6]) - 1.0) < 1e-5 for r in tr)        # unit directions in this scene
+    assert tr[-1][6] == -1 or len(tr) == 6                                    # ends in the sky or at the depth limit
+    assert all(r[6] in (-1.0, 0.0, 1.0) for r in tr)

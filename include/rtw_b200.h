@@ -316,6 +316,16 @@ RTW_API int rtw_accumulator_read(rtw_ctx* ctx, int64_t* out, uint64_t n_values);
 RTW_API int rtw_accumulator_write(rtw_ctx* ctx, const int64_t* in, uint64_t n_values, int image_width, int samples_done,
                                   int samples_total);
 
+/*
+ * The same checkpoint as a self-describing file ("RTWCKPT1": width, samples done / planned, fixed-point scale, and the
+ * seed, max_depth, camera and scene the samples were traced with, CRC-32).  rtw_checkpoint_load needs the scene to be
+ * set already and refuses a file that belongs to another scene (RTW_E_INVALID_ARG) or is damaged (RTW_E_FORMAT); after
+ * it, rtw_accumulate continues at the saved sample and -- unlike after rtw_accumulator_write, whose raw sums carry no
+ * metadata -- must be given the seed, max_depth and camera of the file.
+ */
+RTW_API int rtw_checkpoint_save(rtw_ctx* ctx, const char* path);
+RTW_API int rtw_checkpoint_load(rtw_ctx* ctx, const char* path);
+
 /* ---- image and scene files (host side; no device needed) ---------------------------------------- */
 
 /* binary PPM (P6) / PNG (8-bit RGB, stored deflate blocks) of a row-major 8-bit image, top row first */

@@ -40,6 +40,8 @@ EXPORTED_SYMBOLS = (
     "rtw_progress",
     "rtw_accumulator_read",
     "rtw_accumulator_write",
+    "rtw_checkpoint_save",
+    "rtw_checkpoint_load",
     "rtw_write_ppm",
     "rtw_write_png",
     "rtw_scene_save",
@@ -224,6 +226,10 @@ def load() -> C.CDLL:
     lib.rtw_accumulator_read.argtypes = [vp, i64p, u64]
     lib.rtw_accumulator_write.restype = i32
     lib.rtw_accumulator_write.argtypes = [vp, i64p, u64, i32, i32, i32]
+    lib.rtw_checkpoint_save.restype = i32
+    lib.rtw_checkpoint_save.argtypes = [vp, C.c_char_p]
+    lib.rtw_checkpoint_load.restype = i32
+    lib.rtw_checkpoint_load.argtypes = [vp, C.c_char_p]
     lib.rtw_write_ppm.restype = i32
     lib.rtw_write_ppm.argtypes = [C.c_char_p, u8p, i32, i32]
     lib.rtw_write_png.restype = i32

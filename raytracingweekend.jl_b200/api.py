@@ -238,6 +238,14 @@ class Renderer:
         self._check(self._lib.rtw_accumulator_write(self._ctx, acc.ctypes.data_as(C.POINTER(C.c_int64)), acc.size,
                                                     int(image_width), int(samples_done), int(samples_total)))
 
+    def checkpoint_save(self, path) -> None:
+        """The progressive image as a self-describing file (sums + what they were traced with + CRC-32)."""
+        self._check(self._lib.rtw_checkpoint_save(self._ctx, str(path).encode()))
+
+    def checkpoint_load(self, path) -> None:
+        """Resume from a checkpoint file; the scene it was rendered from must be set already."""
+        self._check(self._lib.rtw_checkpoint_load(self._ctx, str(path).encode()))
+
     # -- device-resident variants (plain device pointers; used with torch tensors as plumbing)
     def render_rows_device(self, cam: Camera, image_width: int, n_samples: int, d_tile_ptr: int, *, max_depth: int =
                            DEFAULT_MAX_DEPTH, seed: int = DEFAULT_SEED, row_start: int = 0, row_stride: int = 1,

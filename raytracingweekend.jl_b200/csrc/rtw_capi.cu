@@ -112,6 +112,7 @@ struct rtw_ctx {
     std::vector<float> h_geom;  // host copy of geom4, kept for the lazy grid build
     std::vector<float> h_mat;   // host copies of mat4 / kind: rtw_set_scene with an unchanged scene is a no-op
     std::vector<uint32_t> h_kind;
+    uint64_t scene_hash = 0;    // FNV-1a of the flattened scene (checkpoint files are tied to it)
     int small_render = 1;       // RTW_OPT_SMALL_RENDER: small renders take the single-launch latency path
     float max_albedo = 0.f;     // largest albedo component of the scene (fixed-point head-room check)
     double max_albedo64 = 0.0;  // the same for the Float64 scene
@@ -146,6 +147,29 @@ constexpr int kDefaultRaysPerLane = 1;
 constexpr int kDefaultSweep = RTW_SWEEP_PACKED;
 constexpr int kDefaultCoop = 2;
 constexpr int kDefaultTail = RTW_TAIL_UNIFIED;
+
+uint64_t fnv1a(const void* data, size_t bytes, uint64_t h) {
+    const unsigned char* p = (const unsigned char*)data;
+    for (size_t i = 0; i < bytes; ++i) h = (h ^ p[i]) * 1099511628211ull;
+    return h;
+}
+
+uint32_t crc32_of(const void* data, size_t bytes, uint32_t crc) {  // CRC-32 (zlib polynomial), continuing from `crc`
+    static uint32_t table[256];
+    static bool ready = false;
+    if (!ready) {
+        for (uint32_t n = 0; n < 256; ++n) {
+            uint32_t c = n;
+            for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            table[n] = c;
+        }
+        ready = true;
+    }
+    const unsigned char* p = (const unsigned char*)data;
+    uint32_t c = crc ^ 0xFFFFFFFFu;
+    for (size_t i = 0; i < bytes; ++i) c = table[(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+    return c ^ 0xFFFFFFFFu;
+}
 
 #ifdef RTW_BUILD_VARIANTS
 constexpr bool kHaveVariants = true;
@@ -710,6 +734,7 @@ int set_scene_locked(rtw_ctx* ctx, const float* geom4, const float* mat4, const 
     ctx->h_geom.assign(geom4, geom4 + 4 * (size_t)n);  // for the lazy grid build (RTW_MODE_GRID only)
     ctx->h_mat.assign(mat4, mat4 + 4 * (size_t)n);
     ctx->h_kind.assign(kind, kind + (size_t)n);
+    ctx->scene_hash = fnv1a(kind, 4 * (size_t)n, fnv1a(mat4, 16 * (size_t)n, fnv1a(geom4, 16 * (size_t)n, 1469598103934665603ull)));
     ctx->max_albedo = max_albedo;
     // pair layout of the geometry for the packed sweep: spheres (2p, 2p+1) -> {xa,xb,ya,yb}{za,zb,ra,rb}
     std::vector<float> pairs((size_t)((n + 1u) / 2u) * 8u, 0.0f);
@@ -1561,8 +1586,7 @@ int rtw_accumulate(rtw_ctx* ctx, const rtw_camera* cam, int image_width, int sam
         if (sample_first < 0 || sample_count < 1 || sample_first > n_samples_total - sample_count)
             return fail(ctx, RTW_E_INVALID_ARG, "samples must satisfy 0 <= first, 1 <= count, first + count <= total");
         ProgressiveState& pg = ctx->prog;
-        uint64_t cam_hash = 1469598103934665603ull;  // FNV-1a over the 88 bytes of the camera
-        for (size_t i = 0; i < sizeof(rtw_camera); ++i) cam_hash = (cam_hash ^ ((const unsigned char*)cam)[i]) * 1099511628211ull;
+        const uint64_t cam_hash = fnv1a(cam, sizeof(rtw_camera), 1469598103934665603ull);  // the 88 bytes of the camera
         if (sample_first != 0) {
             if (!pg.valid || pg.W != image_width || pg.s_total != n_samples_total || pg.s_done != sample_first)
                 return fail(ctx, RTW_E_INVALID_ARG, "sample_first must continue the progressive image held by the context "
@@ -1685,6 +1709,85 @@ int rtw_accumulator_write(rtw_ctx* ctx, const int64_t* in, uint64_t n_values, in
         return RTW_OK;
     } catch (...) {
         return fail(ctx, RTW_E_INTERNAL, "unexpected C++ exception in rtw_accumulator_write");
+    }
+}
+
+/* checkpoint file, little endian:
+ *    0 char[8] "RTWCKPT1"      8 i32 W   12 i32 H   16 i32 samples_done   20 i32 samples_total   24 i32 fx_bits
+ *   28 i32 max_depth   32 u32 have_inputs   36 u32 n_spheres   40 u64 seed   48 u64 camera hash   56 u64 scene hash
+ *   64 i64[H*W*4] fixed-point sums, row-major [row][col][r,g,b,unused]      then u32 CRC-32 of all preceding bytes */
+struct CkptHeader {
+    char magic[8];
+    int32_t W, H, s_done, s_total, fx_bits, max_depth;
+    uint32_t have_inputs, n_spheres;
+    uint64_t seed, cam_hash, scene_hash;
+};
+static_assert(sizeof(CkptHeader) == 64, "checkpoint header layout");
+
+int rtw_checkpoint_save(rtw_ctx* ctx, const char* path) {
+    if (!ctx) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    try {
+        const ProgressiveState& pg = ctx->prog;
+        if (!path) return fail(ctx, RTW_E_INVALID_ARG, "path is NULL");
+        if (!pg.valid) return fail(ctx, RTW_E_INVALID_ARG, "no progressive image: call rtw_accumulate first");
+        CkptHeader h{};
+        std::memcpy(h.magic, "RTWCKPT1", 8);
+        h.W = pg.W; h.H = rtw_image_height(pg.W); h.s_done = pg.s_done; h.s_total = pg.s_total;
+        h.fx_bits = fx_bits_for(pg.s_total);
+        h.max_depth = pg.max_depth; h.have_inputs = pg.have_inputs ? 1u : 0u; h.n_spheres = ctx->n_spheres;
+        h.seed = pg.seed; h.cam_hash = pg.cam_hash; h.scene_hash = ctx->scene_hash;
+        std::vector<int64_t> acc((size_t)h.W * (size_t)h.H * 4);
+        int rc = accumulator_copy(ctx, pg.W, acc.data(), nullptr);
+        if (rc) return rc;
+        uint32_t crc = crc32_of(&h, sizeof h, 0u);
+        crc = crc32_of(acc.data(), acc.size() * sizeof(int64_t), crc);
+        FILE* f = fopen(path, "wb");
+        if (!f) return fail(ctx, RTW_E_IO, "cannot open the checkpoint file for writing");
+        bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+        ok = ok && (acc.empty() || fwrite(acc.data(), sizeof(int64_t), acc.size(), f) == acc.size());
+        ok = ok && fwrite(&crc, 4, 1, f) == 1;
+        ok = (fclose(f) == 0) && ok;
+        return ok ? RTW_OK : fail(ctx, RTW_E_IO, "short write to the checkpoint file");
+    } catch (...) {
+        return fail(ctx, RTW_E_INTERNAL, "unexpected C++ exception in rtw_checkpoint_save");
+    }
+}
+
+int rtw_checkpoint_load(rtw_ctx* ctx, const char* path) {
+    if (!ctx) return RTW_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    try {
+        if (!path) return fail(ctx, RTW_E_INVALID_ARG, "path is NULL");
+        if (!ctx->have_scene) return fail(ctx, RTW_E_NO_SCENE, "set the scene the checkpoint was rendered from first");
+        FILE* f = fopen(path, "rb");
+        if (!f) return fail(ctx, RTW_E_IO, "cannot open the checkpoint file");
+        CkptHeader h{};
+        bool ok = fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, "RTWCKPT1", 8) == 0;
+        ok = ok && h.W >= 1 && h.W <= 65536 && h.H == rtw_image_height(h.W) && h.s_total >= 1 && h.s_total <= (1 << 24) &&
+             h.s_done >= 0 && h.s_done <= h.s_total && h.fx_bits == fx_bits_for(h.s_total);
+        std::vector<int64_t> acc;
+        uint32_t crc_file = 0;
+        if (ok) {
+            acc.resize((size_t)h.W * (size_t)h.H * 4);
+            ok = (acc.empty() || fread(acc.data(), sizeof(int64_t), acc.size(), f) == acc.size()) && fread(&crc_file, 4, 1, f) == 1;
+        }
+        fclose(f);
+        if (!ok) return fail(ctx, RTW_E_FORMAT, "not a checkpoint file of this library (magic, sizes or fixed-point scale)");
+        uint32_t crc = crc32_of(&h, sizeof h, 0u);
+        crc = crc32_of(acc.data(), acc.size() * sizeof(int64_t), crc);
+        if (crc != crc_file) return fail(ctx, RTW_E_FORMAT, "checkpoint checksum does not match");
+        if (h.scene_hash != ctx->scene_hash || h.n_spheres != ctx->n_spheres)
+            return fail(ctx, RTW_E_INVALID_ARG, "the checkpoint belongs to another scene");
+        ctx->prog = ProgressiveState{};
+        int rc = accumulator_copy(ctx, h.W, nullptr, acc.data());
+        if (rc) return rc;
+        ProgressiveState& pg = ctx->prog;
+        pg.valid = true; pg.W = h.W; pg.s_total = h.s_total; pg.s_done = h.s_done;
+        pg.max_depth = h.max_depth; pg.seed = h.seed; pg.cam_hash = h.cam_hash; pg.have_inputs = h.have_inputs != 0;
+        return RTW_OK;
+    } catch (...) {
+        return fail(ctx, RTW_E_INTERNAL, "unexpected C++ exception in rtw_checkpoint_load");
     }
 }
 

@@ -237,6 +237,14 @@ function save_png(ctx::Context, path::AbstractString)
     path
 end
 
+"the progressive image of `ctx` as a self-describing checkpoint file (sums + seed, depth, camera, scene hash + CRC-32)"
+save_checkpoint(ctx::Context, path::AbstractString) =
+    (check(ctx.ptr, ccall((:rtw_checkpoint_save, librtw), Cint, (Ptr{Cvoid}, Cstring), ctx.ptr, path)); path)
+
+"resume from a checkpoint file: `set_scene!` the scene it was rendered from first, then `accumulate!` from its sample on"
+load_checkpoint!(ctx::Context, path::AbstractString) =
+    check(ctx.ptr, ccall((:rtw_checkpoint_load, librtw), Cint, (Ptr{Cvoid}, Cstring), ctx.ptr, path))
+
 "writes the flattened HittableList as a `.rtwscene` file (the fixture format shared with the Python harness / oracle)"
 function save_scene(path::AbstractString, scene::HittableList)
     geom, mat, kind = flatten(scene)
@@ -326,7 +334,7 @@ function install!(; max_depth::Integer = 16, seed::Integer = 1, ctx::Context = d
 end
 
 export render_b200, render_resident, install!, Context, RtwStats, set_option!, set_scene!, accumulate!, resolve, save_png,
-       save_scene, load_scene, scene_random_spheres_device!,
+       save_scene, load_scene, save_checkpoint, load_checkpoint!, scene_random_spheres_device!,
        RTW_OPT_MODE, RTW_OPT_BLOCKS_PER_SM, RTW_OPT_COLLECT_TIMING, RTW_OPT_RAYS_PER_LANE, RTW_OPT_SWEEP, RTW_OPT_COOP,
        RTW_OPT_TAIL, RTW_OPT_WALK, RTW_OPT_GATHER, RTW_OPT_SMALL_RENDER, RTW_MODE_FUSED, RTW_MODE_WAVEFRONT,
        RTW_MODE_CTA_WAVEFRONT, RTW_MODE_GRID, RTW_GATHER_PEER, RTW_GATHER_NCCL

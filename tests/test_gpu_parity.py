@@ -884,3 +884,68 @@ def test_multi_device_gather_peer_and_nccl_identical(rtw, scenes):
         rn.set_option(rtw.RTW_OPT_GATHER, rtw.RTW_GATHER_PEER)
         b2 = np.array(rn.render(cam, 403, 3, max_depth=16, scene=scenes["random"]))
     assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(b2, c2)
+
+
+def test_checkpoint_files_and_pinned_progressive_inputs(rtw, renderer, scenes, tmp_path):
+    # a progressive image is tied to what it was started with: seed, max_depth, camera (continuation passes) and scene
+    # (checkpoint files); the raw-sums checkpoint of rtw_accumulator_write carries none of that, the file does
+    cam, W, total, depth, seed = rtw.t_cam1(), 96, 10, 12, 5
+    renderer.set_scene(scenes["random"])
+    full = np.array(renderer.render(cam, W, total, max_depth=depth, seed=seed))
+    renderer.accumulate(cam, W, 0, 4, total, max_depth=depth, seed=seed)
+    for kw in ({"seed": seed + 1}, {"max_depth": depth + 1}):
+        args = {"max_depth": depth, "seed": seed}
+        args.update(kw)
+        with pytest.raises(rtw.RtwError) as e:
+            renderer.accumulate(cam, W, 4, 6, total, **args)
+        assert e.value.code == rtw._lib.RTW_E_INVALID_ARG
+    with pytest.raises(rtw.RtwError):
+        renderer.accumulate(rtw.t_cam2(), W, 4, 6, total, max_depth=depth, seed=seed)
+    # the failed calls left the image unusable for continuation only if a pass had started: these were refused up front
+    path = tmp_path / "image.rtwckpt"
+    renderer.checkpoint_save(path)
+    assert path.stat().st_size == 64 + 54 * W * 4 * 8 + 4
+    with rtw.Renderer([0]) as r2:
+        with pytest.raises(rtw.RtwError) as e:
+            r2.checkpoint_load(path)  # no scene yet
+        assert e.value.code == rtw._lib.RTW_E_NO_SCENE
+        r2.set_scene(scenes["four"])
+        with pytest.raises(rtw.RtwError) as e:
+            r2.checkpoint_load(path)  # another scene
+        assert e.value.code == rtw._lib.RTW_E_INVALID_ARG
+        r2.set_scene(scenes["random"])
+        r2.checkpoint_load(path)
+        assert r2.progress() == (W, 4, total)
+        with pytest.raises(rtw.RtwError):
+            r2.accumulate(cam, W, 4, 6, total, max_depth=depth, seed=seed + 1)  # the file pins the inputs
+        r2.accumulate(cam, W, 4, 6, total, max_depth=depth, seed=seed)
+        assert np.array_equal(np.array(r2.resolve()), full)
+        blob = bytearray(path.read_bytes())
+        blob[100] ^= 0x40
+        bad = tmp_path / "damaged.rtwckpt"
+        bad.write_bytes(bytes(blob))
+        with pytest.raises(rtw.RtwError) as e:
+            r2.checkpoint_load(bad)
+        assert e.value.code == rtw._lib.RTW_E_FORMAT
+    # a new scene drops the progressive image
+    renderer.set_scene(scenes["four"])
+    with pytest.raises(rtw.RtwError):
+        renderer.resolve()
+
+
+def test_albedo_above_one_is_rendered_within_the_head_room_and_refused_beyond(rtw, oracle, renderer, scenes):
+    # the reference's generic code accepts any albedo; the fixed-point accumulator has 64x head-room per path
+    g, m, k = (a.copy() for a in scenes["four"])
+    m[0, :3] = [2.0, 1.5, 1.0]  # an "emissive" Lambertian
+    cam = rtw.t_default_cam()
+    img = renderer.render(cam, 96, 8, max_depth=6, seed=3, scene=(g, m, k))  # 2^5 = 32 <= 64
+    ref, _, ost = oracle.render(g, m, k, cam.as_array(), 96, 8, max_depth=6, seed=3)
+    assert renderer.last_stats["ray_segments"] == ost["ray_segments"]
+    assert float(np.abs(np.array(img, dtype=np.float64) - ref).max()) < 1e-5 and float(np.array(img).max()) > 1.0
+    with pytest.raises(rtw.RtwError) as e:
+        renderer.render(cam, 96, 8, max_depth=50, seed=3)  # 2^49 does not fit
+    assert e.value.code == rtw._lib.RTW_E_UNSUPPORTED
+    m[1, 0] = np.nan
+    with pytest.raises(rtw.RtwError) as e:
+        renderer.set_scene((g, m, k))
+    assert e.value.code == rtw._lib.RTW_E_UNSUPPORTED

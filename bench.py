@@ -610,8 +610,17 @@ def run_extras(args, R, r, scene, cam, stream, timed_steps, one_step_resident, n
                 best = min(best, time.perf_counter() - t0)
             lat[name] = best * 1e6
             lat[name + "_kernel_launches"] = r.last_stats["kernel_launches"]
+        s64 = R.flatten_scene(R.scene_2_spheres(elem_type=np.float64), np.float64)
+        cam64 = R.t_default_cam(np.float64)
+        for name, s in (("scene_2_spheres_96x54x16_float64", 16), ("scene_2_spheres_96x54x1_float64", 1)):
+            best = 1e9
+            for _ in range(50):  # test/runtests.jl:190-194 as the reference runs it: Float64
+                t0 = time.perf_counter()
+                r.render(cam64, 96, s, scene=s64)
+                best = min(best, time.perf_counter() - t0)
+            lat[name] = best * 1e6
         lat["reference_us"] = {"scene_2_spheres_96x54x1": 101, "scene_2_spheres_96x54x16": 951, "random_spheres_96x54x1": 2040,
-                               "source": "src/proto/proto.jl:87-89, :64-66, :142-144 (Ryzen 3700X, 16 threads, Float64)"}
+                               "source": "src/proto/proto.jl:87-89, :64-66, :142-144 (Ryzen 3700X, 16 threads, Float64 scenes)"}
         out["latency_us"] = lat
     except Exception as e:
         out["latency_us"] = {"error": str(e)}

@@ -45,6 +45,17 @@ def _camera_struct_uncached(cam: Camera) -> rtw_camera:
 
 
 def _camera_struct_f64(cam: Camera) -> rtw_camera_f64:
+    hit = _cam_cache.get(("f64", id(cam)))
+    if hit is not None and hit[0] is cam:
+        return hit[1]
+    c = _camera_struct_f64_uncached(cam)
+    if len(_cam_cache) > 64:
+        _cam_cache.clear()
+    _cam_cache[("f64", id(cam))] = (cam, c)
+    return c
+
+
+def _camera_struct_f64_uncached(cam: Camera) -> rtw_camera_f64:
     c = rtw_camera_f64()
     for name in ("origin", "lower_left_corner", "horizontal", "vertical", "u", "v", "w"):
         getattr(c, name)[:] = [float(x) for x in np.asarray(getattr(cam, name), dtype=F64)]

@@ -73,8 +73,8 @@ struct DeviceState {
     unsigned char* d_gen_ws = nullptr;
     size_t gen_ws_cap = 0;
     // latency path (rtw_small.cu): image and totals in mapped pinned host memory, device counters kept zero between calls
-    float* h_small_img = nullptr;
-    size_t small_img_cap = 0;  // floats
+    void* h_small_img = nullptr;
+    size_t small_img_cap = 0;  // bytes
     unsigned long long* h_small_tot = nullptr;
     bool counters_clean = false;
     // last resident render
@@ -116,6 +116,8 @@ struct rtw_ctx {
     int small_render = 1;       // RTW_OPT_SMALL_RENDER: small renders take the single-launch latency path
     float max_albedo = 0.f;     // largest albedo component of the scene (fixed-point head-room check)
     double max_albedo64 = 0.0;  // the same for the Float64 scene
+    std::vector<double> h_geom64, h_mat64;  // host copies: rtw_set_scene_f64 with an unchanged scene is a no-op
+    std::vector<uint32_t> h_kind64;
     int mode = RTW_MODE_FUSED;
     int rays_per_lane = 0;  // 0 = default
     int sweep = 0;          // 0 = default
@@ -946,6 +948,25 @@ int pass_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int max_depth, uint6
 
 // The latency path: a small render() on one device in ONE kernel launch (rtw_small.cu) -- no memsets, no u/v tables, no
 // resolve kernel, no enqueued copies; the image lands in mapped pinned memory and is memcpy'd to the caller's buffer.
+// mapped pinned image / totals of the latency path, device counters zeroed if a persistent kernel left them dirty
+int small_render_buffers(rtw_ctx* ctx, DeviceState& ds, size_t img_bytes) {
+    if (img_bytes > ds.small_img_cap || !ds.h_small_img) {
+        if (ds.h_small_img) RTW_CUDA(ctx, cudaFreeHost(ds.h_small_img));
+        ds.h_small_img = nullptr;
+        ds.small_img_cap = 0;
+        const size_t cap = std::max<size_t>(img_bytes, 1 << 18);
+        RTW_CUDA(ctx, cudaHostAlloc(&ds.h_small_img, cap, cudaHostAllocMapped));
+        ds.small_img_cap = cap;
+    }
+    if (!ds.h_small_tot) RTW_CUDA(ctx, cudaHostAlloc((void**)&ds.h_small_tot, 64, cudaHostAllocMapped));
+    if (!ds.counters_clean) {
+        RTW_CUDA(ctx, cudaMemsetAsync(ds.d_counters, 0, kCounters * sizeof(unsigned long long), ds.stream));
+        ds.counters_clean = true;  // the kernel leaves them zero
+    }
+    ds.h_small_tot[0] = 0;
+    return RTW_OK;
+}
+
 bool small_render_eligible(const rtw_ctx* ctx, int W, int spp, int max_depth) {
     if (!ctx->small_render || ctx->dev.size() != 1 || ctx->mode != RTW_MODE_FUSED) return false;
     if (ctx->rays_per_lane || ctx->sweep || ctx->coop || ctx->tail || ctx->walk || ctx->blocks_per_sm) return false;  // a variant was asked for
@@ -962,19 +983,8 @@ int small_render_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int spp, int
     const size_t img_floats = (size_t)W * (size_t)H * 3;
     const bool timing = ctx->collect_timing != 0;
     RTW_CUDA(ctx, cudaSetDevice(ds.device));
-    if (img_floats > ds.small_img_cap || !ds.h_small_img) {
-        if (ds.h_small_img) RTW_CUDA(ctx, cudaFreeHost(ds.h_small_img));
-        ds.h_small_img = nullptr;
-        ds.small_img_cap = 0;
-        RTW_CUDA(ctx, cudaHostAlloc((void**)&ds.h_small_img, std::max<size_t>(img_floats, 1 << 16) * sizeof(float), cudaHostAllocMapped));
-        ds.small_img_cap = std::max<size_t>(img_floats, 1 << 16);
-    }
-    if (!ds.h_small_tot) RTW_CUDA(ctx, cudaHostAlloc((void**)&ds.h_small_tot, 64, cudaHostAllocMapped));
-    if (!ds.counters_clean) {
-        RTW_CUDA(ctx, cudaMemsetAsync(ds.d_counters, 0, kCounters * sizeof(unsigned long long), ds.stream));
-        ds.counters_clean = true;  // the kernel leaves them zero
-    }
-    ds.h_small_tot[0] = 0;
+    int rc0 = small_render_buffers(ctx, ds, img_floats * sizeof(float));
+    if (rc0) return rc0;
     rtw::TraceParams p{};
     p.cam = to_dev_camera(cam);
     p.geom = ds.d_geom;
@@ -1050,9 +1060,17 @@ int set_scene_f64_locked(rtw_ctx* ctx, const double* geom4, const double* mat4, 
                     return fail(ctx, RTW_E_UNSUPPORTED, "albedo components must be finite and >= 0 (fixed-point accumulator)");
                 max_albedo = std::max(max_albedo, a);
             }
+    if (ctx->have_scene64 && n == ctx->n_spheres64 && ctx->h_geom64.size() == 4 * (size_t)n &&
+        (n == 0 || (std::memcmp(ctx->h_geom64.data(), geom4, 32 * (size_t)n) == 0 &&
+                    std::memcmp(ctx->h_mat64.data(), mat4, 32 * (size_t)n) == 0 &&
+                    std::memcmp(ctx->h_kind64.data(), kind, 4 * (size_t)n) == 0)))
+        return RTW_OK;  // the same scene again: nothing to upload
     ctx->have_scene64 = false;  // failure-atomic: see set_scene_locked
     ctx->n_spheres64 = 0;
     ctx->max_albedo64 = max_albedo;
+    ctx->h_geom64.assign(geom4, geom4 + 4 * (size_t)n);
+    ctx->h_mat64.assign(mat4, mat4 + 4 * (size_t)n);
+    ctx->h_kind64.assign(kind, kind + (size_t)n);
     for (auto& ds : ctx->dev) {
         RTW_CUDA(ctx, cudaSetDevice(ds.device));
         if (n > ds.scene64_cap || !ds.d_geom64) {
@@ -1097,6 +1115,63 @@ int render_f64_locked(rtw_ctx* ctx, const rtw_camera_f64* cam, int W, int spp, i
     const bool timing = ctx->collect_timing != 0;
     DeviceState& d0 = ctx->dev[0];
     int rc;
+    // the latency path (small_render_f64_kernel): the reference's own smoke test is a 96x54x16 Float64 render
+    if (ctx->small_render && G == 1 && ctx->mode == RTW_MODE_FUSED && ctx->n_spheres64 <= rtw::kTileSpheres && max_depth >= 1 &&
+        H > 0 && (long long)W * H * spp <= (1 << 17) &&
+        (long long)W * H * spp * (long long)std::max<uint32_t>(ctx->n_spheres64, 8u) <= (1ll << 22)) {
+        RTW_CUDA(ctx, cudaSetDevice(d0.device));
+        rc = small_render_buffers(ctx, d0, img_vals * sizeof(double));
+        if (rc) return rc;
+        rtw::TraceParams64 p{};
+        for (int k = 0; k < 3; ++k) {
+            p.cam.origin[k] = cam->origin[k];
+            p.cam.llc[k] = cam->lower_left_corner[k];
+            p.cam.horizontal[k] = cam->horizontal[k];
+            p.cam.vertical[k] = cam->vertical[k];
+            p.cam.u[k] = cam->u[k];
+            p.cam.v[k] = cam->v[k];
+        }
+        p.cam.lens_radius = cam->lens_radius;
+        p.geom = d0.d_geom64; p.mat = d0.d_mat64; p.kind = d0.d_kind64;
+        p.n_spheres = ctx->n_spheres64;
+        p.W = W; p.H = H; p.spp = spp; p.max_depth = max_depth; p.sample_first = 0;
+        p.key0 = (uint32_t)seed; p.key1 = (uint32_t)(seed >> 32);
+        p.row_start = 0; p.row_stride = 1; p.n_rows = H;
+        p.n_paths = (unsigned long long)W * H * spp;
+        p.fx_scale = std::ldexp(1.0, fx_bits);
+        p.counters = d0.d_counters;
+        double* d_img = nullptr;
+        unsigned long long* d_tot = nullptr;
+        RTW_CUDA(ctx, cudaHostGetDevicePointer((void**)&d_img, d0.h_small_img, 0));
+        RTW_CUDA(ctx, cudaHostGetDevicePointer((void**)&d_tot, d0.h_small_tot, 0));
+        rtw::LaunchInfo li{};
+        if (timing) RTW_CUDA(ctx, cudaEventRecord(d0.ev[0], d0.stream));
+        RTW_CUDA(ctx, rtw::launch_small_render_f64(p, std::ldexp(1.0, -fx_bits), d_img, d_tot, d0.stream, &li));
+        if (timing) RTW_CUDA(ctx, cudaEventRecord(d0.ev[1], d0.stream));
+        RTW_CUDA(ctx, cudaStreamSynchronize(d0.stream));
+        std::memcpy(out_rgb, d0.h_small_img, img_vals * sizeof(double));
+        rtw_stats st = {};
+        st.n_spheres = ctx->n_spheres64;
+        st.image_width = W; st.image_height = H; st.rows_rendered = H;
+        st.paths = p.n_paths;
+        st.ray_segments = d0.h_small_tot[0];
+        st.sphere_tests = st.ray_segments * (uint64_t)ctx->n_spheres64;
+        st.kernel_launches = 1;
+        st.n_devices = 1;
+        if (timing) {
+            float ms = 0.f;
+            RTW_CUDA(ctx, cudaEventElapsedTime(&ms, d0.ev[0], d0.ev[1]));
+            st.ms_trace = st.ms_total = ms;
+        }
+        d0.last = st;
+        d0.last_valid = true;
+        d0.last_stream = d0.stream;
+        d0.last_resolved = true;
+        d0.h_counters[1] = st.ray_segments;
+        d0.h_counters[2] = d0.h_counters[3] = 0;
+        if (stats) *stats = st;
+        return RTW_OK;
+    }
     RTW_CUDA(ctx, cudaSetDevice(d0.device));
     rc = grow(ctx, &d0.d_image64, &d0.image64_cap, img_vals);
     if (rc) return rc;

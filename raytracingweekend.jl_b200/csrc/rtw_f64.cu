@@ -424,6 +424,174 @@ __global__ void __launch_bounds__(kTraceBlock, 2) trace_f64_kernel(const __grid_
     if (lane == 0 && seg_count) atomicAdd(P.counters + 1, (unsigned long long)seg_count);
 }
 
+// ---- the latency path in Float64 (the reference's own smoke test renders Float64: test/runtests.jl:188-194) ------------
+// One launch = one whole small render, as small_render_kernel (rtw_small.cu) does for Float32: a pixel is owned by a
+// group of 2^group_log2 adjacent lanes, lane j traces samples j, j + g, ... one path at a time against the list in shared
+// memory (list order, sequential rejection loops -- the code of the reference, line by line), the group adds the
+// fixed-point integers of its paths by shuffle and lane 0 writes sqrt(sum / spp) into mapped host memory; the last CTA
+// publishes the ray-segment count and re-zeroes the device counters.
+constexpr int kSmall64Block = 64;
+
+__global__ void __launch_bounds__(kSmall64Block) small_render_f64_kernel(const __grid_constant__ TraceParams64 P, int group_log2,
+                                                                         double inv_scale, double* __restrict__ out_img,
+                                                                         unsigned long long* __restrict__ host_totals) {
+    extern __shared__ __align__(16) unsigned char smem_small64[];
+    double4* s_list = reinterpret_cast<double4*>(smem_small64);
+    const uint32_t n = P.n_spheres;
+    for (uint32_t i = threadIdx.x; i < n; i += kSmall64Block) s_list[i] = P.geom[i];
+    __syncthreads();
+    const uint32_t g = 1u << group_log2;
+    const unsigned long long gtid = (unsigned long long)blockIdx.x * kSmall64Block + threadIdx.x;
+    const unsigned long long npix = (unsigned long long)P.n_rows * (unsigned long long)P.W;
+    const unsigned long long pl = gtid >> group_log2;
+    const uint32_t j = (uint32_t)gtid & (g - 1u);
+    const bool active = pl < npix;
+    const uint32_t k0 = P.key0, k1 = P.key1;
+    const double tmin = 1e-4;  // T(1e-4), src/ray_color.jl:19
+    long long acc_r = 0, acc_g = 0, acc_b = 0;
+    uint32_t seg_count = 0, i0 = 0, col = 0;
+    if (active) {
+        const uint32_t row_local = (uint32_t)(pl / (unsigned)P.W);
+        col = (uint32_t)(pl - (unsigned long long)row_local * (unsigned)P.W);
+        i0 = (uint32_t)P.row_start + row_local * (uint32_t)P.row_stride;
+        PathRng rng;
+        rng.pixel = i0 * (uint32_t)P.W + col;
+        for (uint32_t s0 = j + (uint32_t)P.sample_first; s0 < (uint32_t)(P.sample_first + P.spp); s0 += g) {  // src/render.jl:29
+            rng.sample = s0;
+            double su = (double)(col + 1u) / (double)P.W;                  // u = T(j/W), src/render.jl:26
+            double sv = (double)((uint32_t)P.H - 1u - i0) / (double)P.H;   // v = T((H-i)/H), src/render.jl:27
+            if (s0 != 0u) {  // src/render.jl:30-36: the first sample is centred; du = draw 0, dv = draw 1
+                const u32x4 b = philox_block(rng, 0u, 0u, k0, k1);
+                su += u01d(b.w0, b.w1) / (double)(float)P.W;
+                sv += u01d(b.w2, b.w3) / (double)(float)P.H;
+            }
+            double px, py;  // get_ray, src/camera.jl:43-48; random_vec2_in_disk (src/rand.jl:31-38) is always drawn
+            for (uint32_t k = 0;; ++k) {
+                const u32x4 b = philox_block(rng, 0u, 1u + k, k0, k1);
+                px = pm1d(b.w0, b.w1);
+                py = pm1d(b.w2, b.w3);
+                if (fma(py, py, px * px) <= 1.0) break;
+            }
+            const DevCamera64& c = P.cam;
+            const double rx = c.lens_radius * px, ry = c.lens_radius * py;
+            const d3 off = mkd(fma(c.v[0], ry, c.u[0] * rx), fma(c.v[1], ry, c.u[1] * rx), fma(c.v[2], ry, c.u[2] * rx));
+            d3 o = mkd(c.origin[0] + off.x, c.origin[1] + off.y, c.origin[2] + off.z);
+            d3 q3;
+            q3.x = fma(sv, c.vertical[0], fma(su, c.horizontal[0], c.llc[0])) - c.origin[0] - off.x;
+            q3.y = fma(sv, c.vertical[1], fma(su, c.horizontal[1], c.llc[1])) - c.origin[1] - off.y;
+            q3.z = fma(sv, c.vertical[2], fma(su, c.horizontal[2], c.llc[2])) - c.origin[2] - off.z;
+            d3 d = normalized(q3);
+            double thr_r = 1.0, thr_g = 1.0, thr_b = 1.0;
+            for (uint32_t nhits = 0;;) {  // ray_color, src/ray_color.jl:14-38, as a loop
+                if ((int)nhits >= P.max_depth) break;
+                double best_t = __longlong_as_double(0x7ff0000000000000ll);  // typemax(T)
+                int best_k = -1;
+                for (uint32_t k = 0; k < n; ++k) {  // hit(::HittableList), src/hit.jl:38-50 + hit(::Sphere), :12-35
+                    const double4 s = s_list[k];
+                    const d3 oc = mkd(o.x - s.x, o.y - s.y, o.z - s.z);
+                    const double hb = dotd(oc, d);
+                    const double cq = fma(-s.w, s.w, dotd(oc, oc));
+                    const double disc = fma(hb, hb, -cq);
+                    if (disc < 0.0) continue;
+                    const double sq = sqrt(disc);
+                    double root = -hb - sq;
+                    if (root < tmin || best_t < root) {
+                        root = -hb + sq;
+                        if (root < tmin || best_t < root) continue;
+                    }
+                    best_t = root;
+                    best_k = (int)k;
+                }
+                seg_count += 1;
+                if (best_k < 0) {  // skycolor, src/ray_color.jl:1-6
+                    const double t = 0.5 * (d.y + 1.0);
+                    const double a = 1.0 - t;
+                    const double sr = a + t * 0.5, sg = a + t * 0.7, sb = a + t;
+                    acc_r += __double2ll_rn(thr_r * sr * P.fx_scale);
+                    acc_g += __double2ll_rn(thr_g * sg * P.fx_scale);
+                    acc_b += __double2ll_rn(thr_b * sb * P.fx_scale);
+                    break;
+                }
+                nhits += 1;
+                if ((int)nhits >= P.max_depth) break;  // the next ray_color call returns black
+                const double4 gs = s_list[best_k];
+                const double4 m = P.mat[best_k];
+                const uint32_t kind = __ldg(P.kind + best_k);
+                const d3 p = mkd(fma(best_t, d.x, o.x), fma(best_t, d.y, o.y), fma(best_t, d.z, o.z));  // hit.jl:3
+                const d3 on = mkd((p.x - gs.x) / gs.w, (p.y - gs.y) / gs.w, (p.z - gs.z) / gs.w);       // hit.jl:33
+                const bool front = dotd(d, on) < 0.0;                                                  // hit.jl:7
+                const d3 nn = front ? on : mkd(-on.x, -on.y, -on.z);
+                d3 nd;
+                if (kind != 2u) {  // Lambertian / Metal: normalize(random_vec3_in_sphere), src/rand.jl:15-22,29
+                    d3 rv;
+                    for (uint32_t a = 0;; ++a) {
+                        const u32x4 b0 = philox_block(rng, nhits, 2u * a, k0, k1);
+                        const u32x4 b1 = philox_block(rng, nhits, 2u * a + 1u, k0, k1);
+                        const d3 q = mkd(pm1d(b0.w0, b0.w1), pm1d(b0.w2, b0.w3), pm1d(b1.w0, b1.w1));
+                        if (dotd(q, q) <= 1.0) { rv = normalized(q); break; }
+                    }
+                    if (kind == 0u) {  // src/material.jl:13-23
+                        const d3 sd = mkd(nn.x + rv.x, nn.y + rv.y, nn.z + rv.z);
+                        nd = dotd(sd, sd) < 1e-5 ? nn : normalized(sd);  // near_zero, src/vec.jl:20
+                    } else {  // src/material.jl:31-34
+                        const d3 refl = reflectd(d, nn);
+                        nd = normalized(mkd(fma(m.w, rv.x, refl.x), fma(m.w, rv.y, refl.y), fma(m.w, rv.z, refl.z)));
+                    }
+                    thr_r *= m.x;
+                    thr_g *= m.y;
+                    thr_b *= m.z;
+                } else {  // Dielectric, src/material.jl:41-53
+                    const double ratio = front ? 1.0 / m.w : m.w;
+                    const double cos_t = fmin(-dotd(d, nn), 1.0);
+                    const double sin_t = sqrt(fma(-cos_t, cos_t, 1.0));
+                    bool reflects = ratio * sin_t > 1.0;
+                    if (!reflects) {  // `||` short-circuits: the coin (draw 3 of the event) only when refraction is possible
+                        const u32x4 b = philox_block(rng, nhits, 1u, k0, k1);
+                        double r0 = (1.0 - ratio) / (1.0 + ratio);  // Schlick, src/light.jl:19-25
+                        r0 = r0 * r0;
+                        const double x = 1.0 - cos_t, x2 = x * x, x4 = x2 * x2;
+                        reflects = fma(1.0 - r0, x4 * x, r0) > u01d(b.w2, b.w3);
+                    }
+                    if (reflects) {
+                        nd = reflectd(d, nn);  // not re-normalised, src/material.jl:48
+                    } else {  // refract, src/light.jl:12-17
+                        const d3 perp = mkd(ratio * fma(cos_t, nn.x, d.x), ratio * fma(cos_t, nn.y, d.y),
+                                            ratio * fma(cos_t, nn.z, d.z));
+                        const double sp = sqrt(fabs(1.0 - dotd(perp, perp)));
+                        nd = normalized(mkd(fma(-sp, nn.x, perp.x), fma(-sp, nn.y, perp.y), fma(-sp, nn.z, perp.z)));
+                    }
+                }
+                o = p;
+                d = nd;
+            }
+        }
+    }
+    for (uint32_t off = g >> 1; off > 0; off >>= 1) {  // integer sums: order-independent
+        acc_r += __shfl_xor_sync(0xffffffffu, acc_r, off);
+        acc_g += __shfl_xor_sync(0xffffffffu, acc_g, off);
+        acc_b += __shfl_xor_sync(0xffffffffu, acc_b, off);
+    }
+    if (active && j == 0u) {
+        const long long at = ((long long)col * P.H + (long long)i0) * 3;  // Julia column-major Matrix{RGB{Float64}}(H, W)
+        const long long a[3] = {acc_r, acc_g, acc_b};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) out_img[at + c] = sqrt((double)a[c] * inv_scale / (double)P.spp);  // render.jl:40, vec.jl:22
+    }
+    for (int off = 16; off > 0; off >>= 1) seg_count += __shfl_xor_sync(0xffffffffu, seg_count, off);
+    if ((threadIdx.x & 31) == 0 && seg_count) atomicAdd(P.counters + 1, (unsigned long long)seg_count);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long done = atomicAdd(P.counters, 1ull) + 1ull;
+        if (done == gridDim.x) {
+            __threadfence();
+            host_totals[0] = atomicExch(P.counters + 1, 0ull);
+            atomicExch(P.counters, 0ull);
+            __threadfence_system();
+        }
+    }
+}
+
 // accum / n_samples -> sqrt (src/render.jl:40, src/vec.jl:22), Float64 out: tile row-major or Julia column-major
 __global__ void __launch_bounds__(256) resolve_f64_kernel(const unsigned long long* __restrict__ accum, int W, int H,
                                                           int n_rows, int row_start, int row_stride, int spp,
@@ -480,6 +648,27 @@ cudaError_t launch_trace_f64(const TraceParams64& p, int num_sms, cudaStream_t s
         info->block = kTraceBlock;
         info->smem_bytes = smem;
         info->blocks_per_sm = per_sm;
+        info->launches = 1;
+        info->rays_per_lane = 1;
+        info->sweep = kSweepBranch;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_small_render_f64(const TraceParams64& p, double inv_scale, double* out_img, unsigned long long* host_totals,
+                                    cudaStream_t stream, LaunchInfo* info) {
+    int group_log2 = 0;
+    while ((1 << group_log2) < p.spp && group_log2 < 5) ++group_log2;
+    const unsigned long long threads = ((unsigned long long)p.n_rows * (unsigned long long)p.W) << group_log2;
+    const unsigned long long blocks = (threads + kSmall64Block - 1) / kSmall64Block;
+    if (blocks == 0 || blocks > 0x7fffffffull) return cudaErrorInvalidValue;
+    const int smem = (int)(p.n_spheres * sizeof(double4));
+    small_render_f64_kernel<<<(unsigned)blocks, kSmall64Block, smem, stream>>>(p, group_log2, inv_scale, out_img, host_totals);
+    if (info) {
+        info->grid = (int)blocks;
+        info->block = kSmall64Block;
+        info->smem_bytes = smem;
+        info->blocks_per_sm = 0;
         info->launches = 1;
         info->rays_per_lane = 1;
         info->sweep = kSweepBranch;

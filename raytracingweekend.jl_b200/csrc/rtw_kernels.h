@@ -156,6 +156,8 @@ cudaError_t launch_scenegen(unsigned long long s0, unsigned long long s1, int ha
                             uint32_t* kind, unsigned long long* out_host, cudaStream_t stream);
 // Float64 path (rtw_f64.cu)
 cudaError_t launch_trace_f64(const TraceParams64& p, int num_sms, cudaStream_t stream, LaunchInfo* info);
+cudaError_t launch_small_render_f64(const TraceParams64& p, double inv_scale, double* out_img, unsigned long long* host_totals,
+                                    cudaStream_t stream, LaunchInfo* info);
 cudaError_t launch_resolve_f64(const unsigned long long* accum, int W, int H, int n_rows, int row_start, int row_stride,
                                int spp, double inv_scale, int column_major, double* out, cudaStream_t stream);
 cudaError_t launch_assemble_f64(const double* tiles, int n_tiles, int W, int H, double* out, cudaStream_t stream);

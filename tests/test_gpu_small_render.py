@@ -95,3 +95,24 @@ def test_device_scene_generator_reproduces_the_host_builder(rtw, fast, half):
     a = np.array(fast.render(cam, 64, 2, max_depth=8))
     b = np.array(fast.render(cam, 64, 2, max_depth=8, scene=(g_ref, m_ref, k_ref)))
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name,cam_name,W,spp,depth", [("two", "default", 96, 16, 16),   # test/runtests.jl:190-194, as is
+                                                       ("two", "default", 96, 1, 16),
+                                                       ("diel", "cam2", 64, 33, 16), ("bubble", "default", 50, 7, 50),
+                                                       ("random", "cam1", 40, 3, 12)])
+def test_small_render_float64(rtw, oracle, renderer, fast, name, cam_name, W, spp, depth):
+    # the reference's own smoke test renders Float64: the Float64 latency path against the Float64 oracle and against the
+    # persistent Float64 kernel
+    from test_gpu_parity import _f64_scene
+    scene = rtw.flatten_scene(_f64_scene(rtw, name), np.float64)
+    cam = {"default": rtw.t_default_cam, "cam1": rtw.t_cam1, "cam2": rtw.t_cam2}[cam_name](np.float64)
+    img = np.array(fast.render(cam, W, spp, max_depth=depth, seed=4, scene=scene))
+    st = dict(fast.last_stats)
+    assert st["kernel_launches"] == 1 and img.dtype == np.float64
+    big = np.array(renderer.render(cam, W, spp, max_depth=depth, seed=4, scene=scene))
+    assert renderer.last_stats["kernel_launches"] >= 2 and renderer.last_stats["ray_segments"] == st["ray_segments"]
+    assert np.array_equal(img, big)
+    ref, _, ost = oracle.render(*scene, cam.as_array(), W, spp, max_depth=depth, seed=4, f64=True)
+    assert st["ray_segments"] == ost["ray_segments"]
+    assert float(np.abs(img - ref).max()) <= 1e-9

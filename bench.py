@@ -530,6 +530,16 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def grid_work_model(st) -> dict:
+    """RTW_MODE_GRID has no linear-sweep work model; its own: cells walked and sphere tests made per ray segment (device
+    counters), against the n_spheres tests per segment of the linear sweep."""
+    segs = max(1, st["ray_segments"])
+    return {"cells_per_segment": st["grid_cells"] / segs, "tests_per_segment": st["grid_tests"] / segs,
+            "linear_sweep_tests_per_segment": st["n_spheres"],
+            "tests_saved_factor": st["n_spheres"] * segs / max(1, st["grid_tests"]),
+            "Mtests_per_s": st["grid_tests"] / (st["ms_trace"] * 1e-3) / 1e6 if st["ms_trace"] else None}
+
+
 def run_extras(args, R, r, scene, cam, stream, timed_steps, one_step_resident, n_spheres) -> dict:
     """N = 1 side measurements on the same GPU: RTW_MODE_GRID on the headline workload, BASELINE configs[4] (100k
     spheres, 1920x1080x256 spp) through the grid, the Float64 instantiation, and the small-render latency."""
@@ -544,6 +554,7 @@ def run_extras(args, R, r, scene, cam, stream, timed_steps, one_step_resident, n
         out["grid_mode"] = {"value": g_segs / (sum(g_ms) * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": sum(g_ms) / 2, "steps": 2,
                             "grid_fallback_rays_per_step": r.stats().get("grid_fallback_rays"),
                             "grid_loose_cells_per_step": r.stats().get("grid_loose_cells"),
+                            "work_model": grid_work_model(r.stats()),
                             "note": "RTW_MODE_GRID: uniform-grid traversal instead of the linear sweep, bit-identical image; "
                                     "not the benchmarked path (no linear-sweep roofline applies)"}
     except Exception as e:  # the headline must not depend on the optional mode
@@ -574,6 +585,7 @@ def run_extras(args, R, r, scene, cam, stream, timed_steps, one_step_resident, n
                             "n_spheres": len(big[2]), "spp": 256, "scene_generation_s": t_gen, "scene_generator": gen,
                             "grid_fallback_rays_per_step": st5.get("grid_fallback_rays"),
                             "grid_loose_cells_per_step": st5.get("grid_loose_cells"),
+                            "work_model": grid_work_model(st5),
                             "equivalent_linear_sweep_T_instr_s": segs5 / 2 * len(big[2]) * FP32_INSTR_PER_TEST / (sum(ms5) / 2 * 1e-3) / 1e12,
                             "workload": f"BASELINE configs[4]: {len(big[2])} spheres, {W}x{R.image_height(W)}, 256 spp, depth {depth}, RTW_MODE_GRID"}
     except Exception as e:

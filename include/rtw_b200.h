@@ -90,6 +90,9 @@ typedef struct rtw_stats {
     uint64_t grid_fallback_rays; /* RTW_MODE_GRID: ray segments no registration margin covers (non-unit direction after
                                     a glass reflection, flying far), resolved by the exact whole-list sweep     */
     uint64_t grid_loose_cells;   /* RTW_MODE_GRID: cells walked with the loose registration (far part of long flights) */
+    uint64_t grid_cells;         /* RTW_MODE_GRID work model: cells walked by all rays ...                        */
+    uint64_t grid_tests;         /* ... and ray-sphere tests made in them and on the big spheres (the exact sweeps of
+                                    grid_fallback_rays are not included)                                          */
 } rtw_stats;
 
 typedef struct rtw_ctx rtw_ctx;

@@ -148,6 +148,8 @@ class rtw_stats(C.Structure):
         ("reserved0", C.c_int32),
         ("grid_fallback_rays", C.c_uint64),
         ("grid_loose_cells", C.c_uint64),
+        ("grid_cells", C.c_uint64),
+        ("grid_tests", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:

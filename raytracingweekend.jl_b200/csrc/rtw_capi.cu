@@ -144,7 +144,7 @@ namespace {
 // defaults chosen by measurement on B200 (profiles/): see DESIGN.md "Kernel variants"
 // device counters: [0] path tickets, [1] ray segments, [2] rays RTW_MODE_GRID resolved by the exact fallback sweep, [3] spare;
 // the pinned host mirror has 2 * kCounters words (the upper half is scratch of RTW_MODE_WAVEFRONT)
-constexpr int kCounters = 4;
+constexpr int kCounters = 8;  // [4] cells walked, [5] sphere tests made in RTW_MODE_GRID; [6], [7] spare
 constexpr int kDefaultRaysPerLane = 1;
 constexpr int kDefaultSweep = RTW_SWEEP_PACKED;
 constexpr int kDefaultCoop = 2;
@@ -497,6 +497,8 @@ int finish_stats(rtw_ctx* ctx, DeviceState& ds, bool timing) {
     ds.last.ray_segments = ds.h_counters[1];
     ds.last.grid_fallback_rays = ds.h_counters[2];
     ds.last.grid_loose_cells = ds.h_counters[3];
+    ds.last.grid_cells = ds.h_counters[4];
+    ds.last.grid_tests = ds.h_counters[5];
     ds.last.sphere_tests = ds.last.ray_segments * (uint64_t)ctx->n_spheres;
     if (timing && ds.last.rows_rendered > 0) {
         float a = 0.f, b = 0.f;
@@ -832,8 +834,7 @@ int pass_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int max_depth, uint6
             ds.last.image_height = H;
             ds.last_resolved = false;
             ds.h_counters[1] = 0;
-            ds.h_counters[2] = 0;
-            ds.h_counters[3] = 0;
+            for (int i = 2; i < kCounters; ++i) ds.h_counters[i] = 0;
         }
     }
     if (do_resolve) {
@@ -926,6 +927,8 @@ int pass_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int max_depth, uint6
         total.ray_segments += ds.last.ray_segments;
         total.grid_fallback_rays += ds.last.grid_fallback_rays;
         total.grid_loose_cells += ds.last.grid_loose_cells;
+        total.grid_cells += ds.last.grid_cells;
+        total.grid_tests += ds.last.grid_tests;
         total.sphere_tests += ds.last.sphere_tests;
         total.rows_rendered += ds.last.rows_rendered;
         total.kernel_launches += ds.last.kernel_launches;
@@ -1029,7 +1032,7 @@ int small_render_locked(rtw_ctx* ctx, const rtw_camera* cam, int W, int spp, int
     ds.last_stream = ds.stream;
     ds.last_resolved = true;
     ds.h_counters[1] = st.ray_segments;  // rtw_last_stats re-reads the pinned mirror
-    ds.h_counters[2] = ds.h_counters[3] = 0;
+    for (int i = 2; i < kCounters; ++i) ds.h_counters[i] = 0;
     if (stats) *stats = st;
     return RTW_OK;
 }
@@ -1168,7 +1171,7 @@ int render_f64_locked(rtw_ctx* ctx, const rtw_camera_f64* cam, int W, int spp, i
         d0.last_stream = d0.stream;
         d0.last_resolved = true;
         d0.h_counters[1] = st.ray_segments;
-        d0.h_counters[2] = d0.h_counters[3] = 0;
+        for (int i = 2; i < kCounters; ++i) d0.h_counters[i] = 0;
         if (stats) *stats = st;
         return RTW_OK;
     }

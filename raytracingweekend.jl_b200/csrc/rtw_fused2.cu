@@ -499,6 +499,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) fused_trace2_kernel(const 
     uint32_t seg_count = 0;
     uint32_t fb_count = 0;  // kGrid: rays of this warp resolved by the exact fallback sweep (uniform)
     uint32_t loose_count = 0;  // kGrid: cells this lane walked with the loose registration
+    uint32_t cell_count = 0, test_count = 0;  // kGrid: cells walked / sphere tests made by this lane (the mode's work model)
     unsigned long long pool_next = 0, pool_end = 0;  // warp-level ticket pool (uniform)
     bool exhausted = false;
 
@@ -721,7 +722,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) fused_trace2_kernel(const 
         best_t = __int_as_float(0x7f800000);  // typemax(T) = Inf, src/ray_color.jl:19
         best_k = -1;
         if (kGrid) {
-            const bool unsafe = closest_hit_grid(P.grid, P.geom, o, d, alive, best_t, best_k, loose_count);
+            const bool unsafe = closest_hit_grid(P.grid, P.geom, o, d, alive, best_t, best_k, loose_count, cell_count, test_count);
             // rays the grid cannot answer exactly (non-unit direction after a glass reflection, very long flights):
             // warp-cooperative sweep of the whole list, for every list size -- the mode is exact by construction
             fb_count += grid_fallback_sweep(P.grid.cull, P.geom, n, o, d, unsafe, best_t, best_k);
@@ -781,6 +782,15 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) fused_trace2_kernel(const 
     if (kGrid) {
         for (int off = 16; off > 0; off >>= 1) loose_count += __shfl_xor_sync(kFullMask, loose_count, off);
         if (lane == 0 && loose_count) atomicAdd(P.counters + 3, (unsigned long long)loose_count);
+        unsigned long long cc = cell_count, tc = test_count;  // 64-bit: a lane can pass 2^32 tests in a long render
+        for (int off = 16; off > 0; off >>= 1) {
+            cc += __shfl_xor_sync(kFullMask, cc, off);
+            tc += __shfl_xor_sync(kFullMask, tc, off);
+        }
+        if (lane == 0) {
+            atomicAdd(P.counters + 4, cc);
+            atomicAdd(P.counters + 5, tc);
+        }
     }
 }
 

@@ -59,10 +59,11 @@ __device__ __forceinline__ void grid_test_sphere(const float4 s, uint32_t k, con
 // hold is: every sphere whose APPARENT extent (radius sqrt(r^2 + eps m^2) at distance m, header) reaches a visited cell
 // was registered there.  The margin that takes grows with the distance, so the registration is chosen per cell from
 // the parameter at which the ray leaves it: tight while eps t^2 stays below safe2_tight, loose while below
-// safe2_loose, and beyond that the ray is unsafe.  `loose_cells` counts the cells walked with the loose lists.
+// safe2_loose, and beyond that the ray is unsafe.  Work counters of this lane: `cells` walked (`loose_cells` of them with
+// the loose lists) and sphere `tests` made (big spheres + the lists of the cells).
 __device__ __forceinline__ bool closest_hit_grid(const GridParams& G, const float4* __restrict__ geom, const f3 o,
                                                  const f3 d, const bool alive, float& best_t, int& best_k,
-                                                 uint32_t& loose_cells) {
+                                                 uint32_t& loose_cells, uint32_t& cells, uint32_t& tests) {
     float bt = __int_as_float(0x7f800000);  // typemax(T) = Inf, src/ray_color.jl:19
     int bk = -1;
     bool unsafe = false;
@@ -71,6 +72,7 @@ __device__ __forceinline__ bool closest_hit_grid(const GridParams& G, const floa
             const uint32_t k = __ldg(G.big + i);
             grid_test_sphere(__ldg(geom + k), k, o, d, bt, bk);
         }
+        tests += G.n_big;
     }
     if (alive && G.nx > 0) {
         // ray against the grid box (slabs); a zero direction component gives +-Inf (or NaN when the origin lies
@@ -134,6 +136,8 @@ __device__ __forceinline__ bool closest_hit_grid(const GridParams& G, const floa
                 const uint32_t* __restrict__ it = tight ? G.items_tight : G.items_loose;
                 loose_cells += tight ? 0u : 1u;
                 const uint32_t first = __ldg(cs + cell), last = __ldg(cs + cell + 1u);
+                cells += 1u;
+                tests += last - first;
                 for (uint32_t i = first; i < last; ++i) {
                     const uint32_t k = __ldg(it + i);
                     grid_test_sphere(__ldg(geom + k), k, o, d, bt, bk);

@@ -43,17 +43,19 @@ struct RtwStats
     reserved0::Int32
     grid_fallback_rays::UInt64
     grid_loose_cells::UInt64
+    grid_cells::UInt64
+    grid_tests::UInt64
 end
 
 const RTW_ABI_VERSION = 3
 
 # The ABI passes Julia's own structs: check the layouts once, when the module loads (include/rtw_b200.h:
-# rtw_camera = 22 x f32, rtw_camera_f64 = 22 x f64, rtw_stats = 88 bytes) and that the library speaks this ABI.
+# rtw_camera = 22 x f32, rtw_camera_f64 = 22 x f64, rtw_stats = 104 bytes) and that the library speaks this ABI.
 function __init__()
     @assert isbitstype(Camera{Float32}) && sizeof(Camera{Float32}) == 88 "Camera{Float32} is not the 22 x Float32 the ABI expects"
     @assert isbitstype(Camera{Float64}) && sizeof(Camera{Float64}) == 176 "Camera{Float64} is not the 22 x Float64 the ABI expects"
     @assert fieldnames(Camera{Float32}) == (:origin, :lower_left_corner, :horizontal, :vertical, :u, :v, :w, :lens_radius)
-    @assert sizeof(RtwStats) == 88 "RtwStats does not match rtw_stats"
+    @assert sizeof(RtwStats) == 104 "RtwStats does not match rtw_stats"
     @assert sizeof(RGB{Float32}) == 12 && sizeof(RGB{Float64}) == 24
     v = ccall((:rtw_abi_version, librtw), Cint, ())
     v == RTW_ABI_VERSION || error("librtw_b200.so has ABI version $v, this shim was written for $RTW_ABI_VERSION")

@@ -50,7 +50,7 @@ def test_struct_layouts_match_header_and_julia(rtw):
     body = text[text.index("typedef struct rtw_stats {"):text.index("} rtw_stats;")]
     fields = re.findall(r"\b([a-z_0-9]+);", body)
     assert fields == [n for n, _ in rtw.rtw_stats._fields_]
-    assert C.sizeof(rtw.rtw_stats) == 88
+    assert C.sizeof(rtw.rtw_stats) == 104
     cam = rtw.t_cam1()
     assert cam.as_array().shape == (22,) and cam.as_array().dtype == np.float32
 

@@ -30,4 +30,5 @@ with R.Renderer([0]) as r:
             print(f"  vs linear sweep at {cspp} spp: identical image {bool((a == b).all())}, segments {sa['ray_segments']} / {sb['ray_segments']}, "
                   f"linear trace {sb['ms_trace']:.0f} ms", flush=True)
         print(f"n={len(scene[2])} spp={spp}: trace {st['ms_trace']:.1f} ms  {st['ray_segments'] / st['ms_trace'] / 1e3:.0f} Mrays/s  "
-              f"segments {st['ray_segments']}  loose {st['grid_loose_cells']}  sweep {st['grid_fallback_rays']}", flush=True)
+              f"segments {st['ray_segments']}  loose {st['grid_loose_cells']}  sweep {st['grid_fallback_rays']}  "
+              f"cells/segment {st['grid_cells'] / st['ray_segments']:.2f}  tests/segment {st['grid_tests'] / st['ray_segments']:.2f}", flush=True)

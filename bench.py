@@ -456,7 +456,7 @@ def run_ours(args):
     # ---- extras (N = 1, default mode only), reported beside -- never instead of -- the headline
     extras = {}
     if world == 1 and args.mode == "linear" and not args.no_extras:
-        extras = run_extras(args, R, r, scene, cam, stream, timed_steps, one_step_resident, n_spheres)
+        extras = run_extras(args, R, r, scene, cam, stream, timed_steps, one_step_resident, n_spheres, fp32_peak)
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
@@ -540,7 +540,7 @@ def grid_work_model(st) -> dict:
             "Mtests_per_s": st["grid_tests"] / (st["ms_trace"] * 1e-3) / 1e6 if st["ms_trace"] else None}
 
 
-def run_extras(args, R, r, scene, cam, stream, timed_steps, one_step_resident, n_spheres) -> dict:
+def run_extras(args, R, r, scene, cam, stream, timed_steps, one_step_resident, n_spheres, fp32_peak) -> dict:
     """N = 1 side measurements on the same GPU: RTW_MODE_GRID on the headline workload, BASELINE configs[4] (100k
     spheres, 1920x1080x256 spp) through the grid, the Float64 instantiation, and the small-render latency."""
     import torch
@@ -588,8 +588,36 @@ def run_extras(args, R, r, scene, cam, stream, timed_steps, one_step_resident, n
                             "work_model": grid_work_model(st5),
                             "equivalent_linear_sweep_T_instr_s": segs5 / 2 * len(big[2]) * FP32_INSTR_PER_TEST / (sum(ms5) / 2 * 1e-3) / 1e12,
                             "workload": f"BASELINE configs[4]: {len(big[2])} spheres, {W}x{R.image_height(W)}, 256 spp, depth {depth}, RTW_MODE_GRID"}
+        # the same list through the LINEAR sweep (streamed tiles of 1024 spheres, TMA double buffer) on a 4-spp slice --
+        # the full 256 spp would take ~2 minutes; a short slice also pays the drain of the persistent kernel (the last
+        # 50-bounce paths keep whole warps busy), 16 spp reaches 0.83 -- against the FP32 roofline, and the grid image at
+        # the same spp
+        lspp = 4
+        r.render_rows_device(cam, W, lspp, img.data_ptr(), max_depth=depth, seed=1, column_major=True, stream=stream.cuda_stream)
+        stream.synchronize()
+        sha_grid = image_sha256(img.cpu().numpy())
+        r.set_option(R.RTW_OPT_MODE, R.RTW_MODE_FUSED)
+
+        def step5l():
+            r.render_rows_device(cam, W, lspp, img.data_ptr(), max_depth=depth, seed=1, column_major=True, stream=stream.cuda_stream)
+
+        r.render_rows_device(cam, W, 1, img.data_ptr(), max_depth=depth, seed=1, column_major=True, stream=stream.cuda_stream)  # warm-up
+        ms5l, segs5l, _ = timed_steps(lambda: (step5l(), None)[1], 1)
+        st5l = r.stats()
+        sha_lin = image_sha256(img.cpu().numpy())
+        rate5 = st5l["sphere_tests"] * FP32_INSTR_PER_TEST / (st5l["ms_trace"] * 1e-3)
+        out["cfg5_linear"] = {"value": segs5l / (sum(ms5l) * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": sum(ms5l), "steps": 1,
+                              "n_spheres": len(big[2]), "spp": lspp, "T_fp32_instr_s": rate5 / 1e12,
+                              "frac_of_measured_fp32_peak": rate5 / fp32_peak,
+                              "extrapolated_s_at_256_spp": sum(ms5l) * 1e-3 * 256 / lspp,
+                              "image_sha256": sha_lin, "image_sha256_grid_same_spp": sha_grid,
+                              "workload": f"BASELINE configs[4] slice: {len(big[2])} spheres, {W}x{R.image_height(W)}, {lspp} of 256 spp, "
+                                          f"depth {depth}, linear sweep (streamed tiles)"}
+        if sha_lin != sha_grid:
+            out["cfg5_linear"]["error"] = "grid and linear images differ"
     except Exception as e:
-        out["cfg5_grid"] = {"error": str(e)}
+        out.setdefault("cfg5_grid", {"error": str(e)})
+        out.setdefault("cfg5_linear", {"error": str(e)})
     finally:
         r.set_option(R.RTW_OPT_MODE, R.RTW_MODE_FUSED)
         r.set_scene(scene)

@@ -157,16 +157,18 @@ uint64_t fnv1a(const void* data, size_t bytes, uint64_t h) {
 }
 
 uint32_t crc32_of(const void* data, size_t bytes, uint32_t crc) {  // CRC-32 (zlib polynomial), continuing from `crc`
-    static uint32_t table[256];
-    static bool ready = false;
-    if (!ready) {
-        for (uint32_t n = 0; n < 256; ++n) {
-            uint32_t c = n;
-            for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
-            table[n] = c;
+    struct Table {
+        uint32_t v[256];
+        Table() {
+            for (uint32_t n = 0; n < 256; ++n) {
+                uint32_t c = n;
+                for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+                v[n] = c;
+            }
         }
-        ready = true;
-    }
+    };
+    static const Table tab;  // initialised once, thread-safe (contexts on different threads share it)
+    const uint32_t* table = tab.v;
     const unsigned char* p = (const unsigned char*)data;
     uint32_t c = crc ^ 0xFFFFFFFFu;
     for (size_t i = 0; i < bytes; ++i) c = table[(c ^ p[i]) & 0xFFu] ^ (c >> 8);

@@ -73,7 +73,10 @@ __constant__ uint32_t c_coop_tab[33] = {
     1u | (256u << 8), 1u | (256u << 8)};
 
 // random_between(-1, 1) of the word's uniform (src/rand.jl:24): 2*(k*2^-23) - 1 = k*2^-22 - 1, exact either way
-__device__ __forceinline__ float pm1x(uint32_t w) { return fmaf((float)(w >> 9), 2.384185791015625e-07f, -1.0f); }
+// Two instructions instead of shift + convert + fma: the 23 bits become the mantissa of a float in [2, 4), 2 + k*2^-22, and
+// subtracting 3 is exact (the result is a multiple of 2^-22 below 1 in magnitude).  u01x: the same for k*2^-23 via [1, 2).
+__device__ __forceinline__ float pm1x(uint32_t w) { return __uint_as_float(__funnelshift_r(w, 0x80u, 9)) - 3.0f; }
+__device__ __forceinline__ float u01x(uint32_t w) { return __uint_as_float(__funnelshift_r(w, 0x7fu, 9)) - 1.0f; }
 
 // ---- candidate resolution over the permuted AoS copy ----------------------------------------------------------
 // aos_perm[(c*kCoop + h)*32 + j] = the sphere that lane h of a group tests as its j-th test of super-chunk c, i.e.
@@ -600,13 +603,13 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) fused_trace2_kernel(const 
             const float q23 = fmaf(pw, pw, pz * pz);
             if (newp) {
                 if (s0 != 0u) {  // du = draw 0, dv = draw 1; the first sample is centred
-                    js = su + __fdiv_rn(u01(b0.w0), (float)P.W);
-                    jt = sv + __fdiv_rn(u01(b0.w1), (float)P.H);
+                    js = su + __fdiv_rn(u01x(b0.w0), (float)P.W);
+                    jt = sv + __fdiv_rn(u01x(b0.w1), (float)P.H);
                 }
                 px = pz;  // disk attempt 0 = draws 2, 3 (src/rand.jl:31-38; always drawn, src/camera.jl:44)
                 py = pw;
             } else {
-                coin = u01(b0.w3);
+                coin = u01x(b0.w3);
             }
             need = ball ? !(qball <= 1.0f) : (newp ? !(q23 <= 1.0f) : false);
         }
@@ -616,6 +619,23 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) fused_trace2_kernel(const 
         {
             unsigned needm = __ballot_sync(kFullMask, need);
             uint32_t blk = 1u;  // next unevaluated block; uniform: every needy lane has failed the same attempts
+            if (needm) {
+                // block 1 by the lane itself: after attempt 0 about 40 % of the lanes are in need, so a cooperative pass
+                // would give each of them two helper lanes at the price of the request exchange; one more own block
+                // halves their number for less, and the cooperative passes take over from block 2 with 5+ helpers each
+                const u32x4 hb = philox_block_rk(P, sample, pixel, ev, 1u);
+                float hx = pm1x(hb.w0), hy = pm1x(hb.w1);
+                const float hz = pm1x(hb.w2), hw = pm1x(hb.w3);
+                const float q01 = fmaf(hy, hy, hx * hx);
+                const float qball = fmaf(hz, hz, q01);
+                const float q23 = fmaf(hw, hw, hz * hz);
+                const bool ok01 = q01 <= 1.0f;
+                const float qsel = newp ? fminf(q01, q23) : qball;
+                if (newp & !ok01) { hx = hz; hy = hw; }
+                if (need && qsel <= 1.0f) { px = hx; py = hy; pz = hz; need = false; }
+                blk = 2u;
+                needm = __ballot_sync(kFullMask, need);
+            }
             while (needm) {
                 const uint32_t cnt = (uint32_t)__popc(needm);
                 const uint32_t tab = c_coop_tab[cnt];

@@ -630,8 +630,10 @@ def run_extras(args, R, r, scene, cam, stream, timed_steps, one_step_resident, n
         r.render(cam64, W, spp64, max_depth=depth, scene=s64)
         st = r.last_stats
         rate = st["sphere_tests"] * FP32_INSTR_PER_TEST / (st["ms_trace"] * 1e-3) / 1e12
+        dfma_peak, _ = r.measure_fp32_peak(9)  # independent DFMA chains on every SM, measured live
         out["float64"] = {"value": st["ray_segments"] / (st["ms_trace"] * 1e-3) / 1e6, "unit": UNIT, "spp": spp64,
                           "ms_trace": st["ms_trace"], "T_fp64_instr_s": rate, "frac_of_nominal_dfma": rate / (148 * 64 * 1.965e9 / 1e12),
+                          "measured_dfma_peak_T_instr_s": dfma_peak / 1e12, "frac_of_measured_dfma": rate / (dfma_peak / 1e12),
                           "workload": f"scene_random_spheres(Float64), t_cam1, {W}x{R.image_height(W)}, {spp64} spp, depth {depth}"}
     except Exception as e:
         out["float64"] = {"error": str(e)}

@@ -351,6 +351,7 @@ RTW_API int rtw_scene_load(const char* path, float* geom4, float* mat4, uint32_t
  *   variant 0: pure FFMA;  variant 1: the scalar mask sweep's own mix (3 FADD, 2 FMUL, 6 FFMA + 1 SHF, 1 LDS.128 per test);
  *   variant 2: the packed FP32x2 mask sweep (the same 11 lane-ops per test, two tests per instruction);
  *   variants 3, 4: variant 2 with 2 / 4 cooperating lanes per sphere load (RTW_OPT_COOP)
+ *   variant 9: independent Float64 FMA chains (DFMA) -- the measured denominator of the Float64 kernel's fraction
  * Writes achieved FP32 instructions/s (lane-instructions, i.e. warp instructions x 32) and the kernel time.
  */
 RTW_API int rtw_measure_fp32_peak(rtw_ctx* ctx, int device_slot, int variant, double* fp32_instr_per_s, float* ms);

@@ -1875,7 +1875,7 @@ int rtw_measure_fp32_peak(rtw_ctx* ctx, int device_slot, int variant, double* fp
     if (!ctx || !fp32_instr_per_s) return RTW_E_INVALID_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (device_slot < 0 || device_slot >= (int)ctx->dev.size()) return fail(ctx, RTW_E_INVALID_ARG, "bad device_slot");
-    if (variant < 0 || variant % 10 > 8 || variant / 10 > 8) return fail(ctx, RTW_E_INVALID_ARG, "variant must be 0..4 (+10*L)");
+    if (variant < 0 || variant / 10 > 8) return fail(ctx, RTW_E_INVALID_ARG, "variant must be 0..9 (+10*L)");
     DeviceState& ds = ctx->dev[device_slot];
     RTW_CUDA(ctx, cudaSetDevice(ds.device));
     double instr = 0.0, best = 0.0;

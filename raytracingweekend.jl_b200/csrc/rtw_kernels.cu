@@ -296,6 +296,21 @@ __global__ void __launch_bounds__(kPeakBlock) fp32_peak_ffma_kernel(float* out, 
     if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // never true: keeps the chains alive
 }
 
+// variant 9: the same with Float64 chains -- the measured DFMA rate, denominator of the Float64 kernel's fraction
+__global__ void __launch_bounds__(kPeakBlock) fp64_peak_dfma_kernel(float* out, double b, double c) {
+    double a[kPeakChains];
+#pragma unroll
+    for (int i = 0; i < kPeakChains; ++i) a[i] = (double)(threadIdx.x + i) * 1e-3;
+    for (int it = 0; it < kPeakIters / 4; ++it) {
+#pragma unroll
+        for (int i = 0; i < kPeakChains; ++i) a[i] = fma(a[i], b, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < kPeakChains; ++i) s += a[i];
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s;  // never true: keeps the chains alive
+}
+
 // the sweep's own instruction mix (mask variant: 11 FP32 + 1 SHF per test, 1 LDS.128 per R tests) with no
 // candidate ever resolved; ray data comes from memory so nothing is constant-folded
 template <int R, bool kPacked, int kCoopPeak>
@@ -498,6 +513,10 @@ cudaError_t launch_fp32_peak(int variant, int num_sms, float* scratch, cudaStrea
         case 0:
             fp32_peak_ffma_kernel<<<grid, kPeakBlock, 0, stream>>>(scratch, 0.999f, 1e-4f);
             *fp32_instr = (double)grid * kPeakBlock * (double)kPeakIters * kPeakChains;
+            return cudaGetLastError();
+        case 9:
+            fp64_peak_dfma_kernel<<<grid, kPeakBlock, 0, stream>>>(scratch, 0.999, 1e-4);
+            *fp32_instr = (double)grid * kPeakBlock * (double)(kPeakIters / 4) * kPeakChains;
             return cudaGetLastError();
         case 1: return launch(fp32_peak_sweep_kernel<1, false, 1>);
         case 2: return launch(fp32_peak_sweep_kernel<1, true, 1>);

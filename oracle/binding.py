@@ -82,6 +82,7 @@ def load() -> C.CDLL:
     lib.rtwo_skycolor_f32.argtypes = [f3, d3]
     lib.rtwo_skycolor_f64.argtypes = [d3, d3]
     lib.rtwo_philox4x32_10.argtypes = [u32p, u32p, u32p]
+    lib.rtwo_philox4x32_7.argtypes = [u32p, u32p, u32p]
     lib.rtwo_path_stream_f32.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, f3]
     lib.rtwo_xoroshiro_u64.argtypes = [C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
     lib.rtwo_xoroshiro_f32.argtypes = [C.c_uint64, C.c_int, f3]
@@ -158,6 +159,16 @@ def philox4x32_10(ctr, key):
     k = (C.c_uint32 * 2)(*key)
     out = (C.c_uint32 * 4)()
     lib.rtwo_philox4x32_10(c, k, out)
+    return [int(x) for x in out]
+
+
+def philox4x32_7(ctr, key):
+    """one block of the PRODUCTION stream (Philox4x32-7, RTWO_PHILOX_ROUNDS)"""
+    lib = load()
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    out = (C.c_uint32 * 4)()
+    lib.rtwo_philox4x32_7(c, k, out)
     return [int(x) for x in out]
 
 

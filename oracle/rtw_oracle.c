@@ -17,7 +17,7 @@
 
 typedef struct {
     int mode;
-    /* Philox4x32-10, addressed by (pixel, sample, event, word position) */
+    /* Philox4x32-7, addressed by (pixel, sample, event, word position) */
     uint32_t key[2];
     uint32_t pixel, sample, event;
     uint32_t pos;       /* next word of the current event's word sequence: block = pos / 4, word = pos % 4 */
@@ -33,10 +33,10 @@ typedef struct {
 #define PHILOX_W0 0x9E3779B9u
 #define PHILOX_W1 0xBB67AE85u
 
-void rtwo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+void rtwo_philox4x32(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
     uint32_t k0 = key[0], k1 = key[1];
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < rounds; ++r) {
         uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
         uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -48,6 +48,8 @@ void rtwo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+void rtwo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { rtwo_philox4x32(ctr, key, 10, out); }
+void rtwo_philox4x32_7(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { rtwo_philox4x32(ctr, key, RTWO_PHILOX_ROUNDS, out); }
 
 /*
  * Production stream (documented in DESIGN.md "RNG stream"): every uniform is ADDRESSED, not drawn from a running
@@ -115,7 +117,7 @@ static inline uint32_t rtwo_next_u32(rtwo_rng* g) {
     uint32_t blk = g->pos >> 2;
     if (!g->buf_valid || g->buf_block != blk) {
         uint32_t ctr[4] = {blk, g->sample, g->pixel, g->event};
-        rtwo_philox4x32_10(ctr, g->key, g->buf);
+        rtwo_philox4x32(ctr, g->key, RTWO_PHILOX_ROUNDS, g->buf);
         g->buf_block = blk;
         g->buf_valid = 1;
     }

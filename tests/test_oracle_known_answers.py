@@ -95,6 +95,11 @@ def test_philox_known_answer_vectors(oracle):
     assert oracle.philox4x32_10([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
     assert oracle.philox4x32_10([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == [
         0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+    # ... and for philox4x32-7, the round count of the production stream (RTWO_PHILOX_ROUNDS / kPhiloxRounds)
+    assert oracle.philox4x32_7([0, 0, 0, 0], [0, 0]) == [0x5F6FB709, 0x0D893F64, 0x4F121F81, 0x4F730A48]
+    assert oracle.philox4x32_7([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x5207DDC2, 0x45165E59, 0x4D8EE751, 0x8C52F662]
+    assert oracle.philox4x32_7([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == [
+        0x4DFCCABA, 0x190A87F0, 0xC47362BA, 0xB6B5242A]
 
 
 def test_path_stream_layout(oracle):
@@ -105,7 +110,7 @@ def test_path_stream_layout(oracle):
         got = oracle.path_stream(seed, pixel, sample, event, 12)
         exp = []
         for blk in range(3):
-            exp += [np.float32(w >> 9) * np.float32(2.0 ** -23) for w in oracle.philox4x32_10([blk, sample, pixel, event], key)]
+            exp += [np.float32(w >> 9) * np.float32(2.0 ** -23) for w in oracle.philox4x32_7([blk, sample, pixel, event], key)]
         assert got.tolist() == [float(x) for x in exp]
         assert got.min() >= 0.0 and got.max() < 1.0
 

@@ -921,10 +921,6 @@ cudaError_t launch_fused_trace2(const TraceParams& p, int num_sms, int blocks_pe
     }
     if (blocks_per_sm_override == 2)  // 128 registers per thread, 2 CTAs per SM
         return launch_variant2<false, 4, true, 2>(p, num_sms, blocks_per_sm_override, stream, info);
-    if (blocks_per_sm_override == 20)  // 96 registers per thread, 20 warps per SM as 2 CTAs of 320 threads
-        return launch_variant2<false, 4, true, 2, 320>(p, num_sms, 2, stream, info);
-    if (blocks_per_sm_override == 21)  // 96 registers per thread, 20 warps per SM as 5 CTAs of 128 threads
-        return launch_variant2<false, 4, true, 5, 128>(p, num_sms, 5, stream, info);
     return launch_variant2<false, 4, true>(p, num_sms, blocks_per_sm_override, stream, info);
 #else
     return cudaErrorNotSupported;  // built without RTW_BUILD_VARIANTS=1

@@ -51,7 +51,8 @@ extern "C" {
 
 /* ray_color's default `depth` (src/ray_color.jl:14) -- render() never overrides it (src/render.jl:38) */
 #define RTW_DEFAULT_MAX_DEPTH 16
-/* reseed!() at the top of every render (src/render.jl:21, src/rand.jl:2): same seed => same image */
+/* reseed!() at the top of every render (src/render.jl:21, src/rand.jl:2): same seed => same image (the stream is an
+ * addressed Philox4x32-7 keyed by the seed) */
 #define RTW_DEFAULT_SEED 1ull
 
 /*
@@ -320,7 +321,7 @@ RTW_API int rtw_accumulator_write(rtw_ctx* ctx, const int64_t* in, uint64_t n_va
                                   int samples_total);
 
 /*
- * The same checkpoint as a self-describing file ("RTWCKPT1": width, samples done / planned, fixed-point scale, and the
+ * The same checkpoint as a self-describing file ("RTWCKPT2": width, samples done / planned, fixed-point scale, and the
  * seed, max_depth, camera and scene the samples were traced with, CRC-32).  rtw_checkpoint_load needs the scene to be
  * set already and refuses a file that belongs to another scene (RTW_E_INVALID_ARG) or is damaged (RTW_E_FORMAT); after
  * it, rtw_accumulate continues at the saved sample and -- unlike after rtw_accumulator_write, whose raw sums carry no

@@ -1792,8 +1792,9 @@ int rtw_accumulator_write(rtw_ctx* ctx, const int64_t* in, uint64_t n_values, in
     }
 }
 
-/* checkpoint file, little endian:
- *    0 char[8] "RTWCKPT1"      8 i32 W   12 i32 H   16 i32 samples_done   20 i32 samples_total   24 i32 fx_bits
+/* checkpoint file, little endian ("RTWCKPT2": the sums of the Philox4x32-7 stream; "RTWCKPT1" files hold 10-round sums and are
+ * refused -- continuing them would mix two streams):
+ *    0 char[8] "RTWCKPT2"      8 i32 W   12 i32 H   16 i32 samples_done   20 i32 samples_total   24 i32 fx_bits
  *   28 i32 max_depth   32 u32 have_inputs   36 u32 n_spheres   40 u64 seed   48 u64 camera hash   56 u64 scene hash
  *   64 i64[H*W*4] fixed-point sums, row-major [row][col][r,g,b,unused]      then u32 CRC-32 of all preceding bytes */
 struct CkptHeader {
@@ -1812,7 +1813,7 @@ int rtw_checkpoint_save(rtw_ctx* ctx, const char* path) {
         if (!path) return fail(ctx, RTW_E_INVALID_ARG, "path is NULL");
         if (!pg.valid) return fail(ctx, RTW_E_INVALID_ARG, "no progressive image: call rtw_accumulate first");
         CkptHeader h{};
-        std::memcpy(h.magic, "RTWCKPT1", 8);
+        std::memcpy(h.magic, "RTWCKPT2", 8);
         h.W = pg.W; h.H = rtw_image_height(pg.W); h.s_done = pg.s_done; h.s_total = pg.s_total;
         h.fx_bits = fx_bits_for(pg.s_total);
         h.max_depth = pg.max_depth; h.have_inputs = pg.have_inputs ? 1u : 0u; h.n_spheres = ctx->n_spheres;
@@ -1843,7 +1844,7 @@ int rtw_checkpoint_load(rtw_ctx* ctx, const char* path) {
         FILE* f = fopen(path, "rb");
         if (!f) return fail(ctx, RTW_E_IO, "cannot open the checkpoint file");
         CkptHeader h{};
-        bool ok = fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, "RTWCKPT1", 8) == 0;
+        bool ok = fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, "RTWCKPT2", 8) == 0;
         ok = ok && h.W >= 1 && h.W <= 65536 && h.H == rtw_image_height(h.W) && h.s_total >= 1 && h.s_total <= (1 << 24) &&
              h.s_done >= 0 && h.s_done <= h.s_total && h.fx_bits == fx_bits_for(h.s_total);
         std::vector<int64_t> acc;
